@@ -1,0 +1,302 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (imported by path, CPU fp32).
+
+Run in the authoring container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+The reference has no golden vectors of its own; these fixtures are what pins the
+oracle (tests/test_oracle_golden.py) and, through it and directly, the CUDA kernels
+(tests/test_gpu_*.py).  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name, B, H, Hkv, T, S, d, causal, left_pad (per sample), right_pad, active, multi_head
+ATTN_CASES = [
+    ("causal_square",      2, 4, 4, 48, 48, 32, True,  None,   None,   True,  True),
+    ("causal_square_d128", 1, 2, 2, 160, 160, 128, True, None,  None,   True,  True),
+    ("left_pad",           2, 4, 4, 40, 40, 32, True,  [0, 7], None,   True,  True),
+    ("right_pad",          2, 4, 4, 40, 40, 32, True,  None,   [3, 0], True,  True),
+    ("key_holes",          2, 4, 4, 40, 40, 32, True,  "holes", None,  True,  True),
+    ("gqa_group4",         2, 8, 2, 36, 36, 32, True,  None,   None,   True,  True),
+    ("kv_cache_T_lt_S",    2, 4, 4, 5,  37, 32, True,  None,   None,   True,  True),
+    ("decode_T1",          2, 4, 4, 1,  33, 32, False, None,   None,   True,  True),
+    ("inactive",           2, 4, 4, 48, 48, 32, True,  None,   None,   False, True),
+    ("single_head_mu",     2, 4, 4, 24, 24, 32, True,  None,   None,   True,  False),
+    ("d64_ragged",         1, 3, 3, 77, 77, 64, True,  None,   None,   True,  True),
+]
+
+
+def key_mask_for(case, B, S):
+    name, *_rest = case
+    left, right = case[8], case[9]
+    km = torch.ones(B, S, dtype=torch.bool)
+    if isinstance(left, str) and left == "holes":
+        # PAD separators in the middle of the row, like ShiftModel's "ICE [PAD] query [PAD] answer"
+        km[0, 11] = False
+        km[0, 25] = False
+        km[1, :4] = False
+        km[1, 17] = False
+    elif left is not None:
+        for b, n in enumerate(left):
+            km[b, :n] = False
+    if right is not None:
+        for b, n in enumerate(right):
+            if n:
+                km[b, S - n:] = False
+    return km
+
+
+def run_attn_case(case, seed):
+    se = ref_loader.load_shift_encoder()
+    name, B, H, Hkv, T, S, d, causal, _l, _r, active, multi_head = case
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, H, T, d, generator=g)
+    k = torch.randn(B, Hkv, S, d, generator=g)
+    v = torch.randn(B, Hkv, S, d, generator=g)
+    d_out = torch.randn(B, T, H, d, generator=g)
+    strategy = ref_loader.MIMIC_ATTN if multi_head else \
+        "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE"
+    enc = ref_loader.make_ref_encoder(H * d, 2, H, attn_strategy=strategy)
+    layer = 1
+    with torch.no_grad():                       # "trained-like" values so mu is not ~0
+        enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.5)
+        for lin in enc.log_Z1_lin:
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.2)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g))
+    enc.attn_shift_handles[layer].active = active
+    km = key_mask_for(case, B, S)
+
+    q_, k_, v_ = (t.clone().requires_grad_(True) for t in (q, k, v))
+    G = H // Hkv
+    kk = k_[:, :, None].expand(B, Hkv, G, S, d).reshape(B, H, S, d)      # HF repeat_kv
+    vv = v_[:, :, None].expand(B, Hkv, G, S, d).reshape(B, H, S, d)
+    plain_causal = causal and bool(km.all()) and T == S
+    if plain_causal:                            # reference: mask None -> is_causal (348-350 / 447)
+        attn = F.scaled_dot_product_attention(q_, kk, vv, attn_mask=None, is_causal=T > 1)
+        row_valid = torch.ones(B, T, dtype=torch.bool)
+    else:                                       # reference: explicit 4-D mask from HF, is_causal False
+        s_idx = torch.arange(S)[None, None, None, :]
+        t_idx = torch.arange(T)[None, None, :, None]
+        mask = km[:, None, None, :].expand(B, 1, T, S).clone()
+        if causal:
+            mask &= s_idx <= t_idx + (S - T)
+        row_valid = mask.any(-1)[:, 0]          # rows with no visible key: reference undefined
+        add = torch.zeros(B, 1, T, S).masked_fill(~mask, torch.finfo(torch.float32).min)
+        attn = F.scaled_dot_product_attention(q_, kk, vv, attn_mask=add, is_causal=False)
+    attn_t = attn.transpose(1, 2)
+    out = enc.do_shift(layer, q_, kk, attn_t)   # THE reference call
+    out = out.reshape(B, T, H, d)
+    d_out = d_out * row_valid[:, :, None, None]  # fully-masked rows never reach a loss
+    params = [enc.attn_shift] + [p for p in enc.log_Z1_lin[layer].parameters()]
+    grads = torch.autograd.grad(out, [q_, k_, v_] + params, d_out, allow_unused=True)
+    dq, dk, dv, dshift_all, dw, db = grads
+    rec = dict(
+        q=q, k=k, v=v, d_out=d_out, key_mask=km, row_valid=row_valid,
+        shift=enc.attn_shift[layer].detach().reshape(-1), w=enc.log_Z1_lin[layer].weight.detach(),
+        b=enc.log_Z1_lin[layer].bias.detach(), out=out.detach(), dq=dq, dk=dk, dv=dv,
+        meta=np.array([B, H, Hkv, T, S, d, int(causal), int(active), int(multi_head)], dtype=np.int64),
+    )
+    if active:
+        rec.update(dshift=dshift_all[layer].reshape(-1), dw=dw, db=db)
+    return {k_: (v_.numpy() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in rec.items()}
+
+
+def gen_attention():
+    for i, case in enumerate(ATTN_CASES):
+        rec = run_attn_case(case, 3407 + i)
+        np.savez_compressed(os.path.join(OUT, f"attn_{case[0]}.npz"), **rec)
+        print("attn", case[0], "out-norm", float(np.linalg.norm(rec["out"])))
+
+
+# ---------------------------------------------------------------- shift_model pieces
+
+class _Tok:
+    pad_token_id, bos_token_id, eos_token_id, padding_side = 0, 1, 2, "left"
+    pad_token, eos_token = "<pad>", "</s>"
+
+
+def make_ref_shift_model(enc, strategy_str="Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE"):
+    sm = ref_loader.load_shift_model()
+    enc.lmm.processor = types.SimpleNamespace(tokenizer=_Tok())
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0,
+                                data=types.SimpleNamespace(num_image_in_query=1))
+    return sm.ShiftModel(cfg, enc, eval(strategy_str, {"Strategy": sm.Strategy})), sm
+
+
+def gen_loss_pieces():
+    enc = ref_loader.make_ref_encoder(64, 3, 4)
+    model, sm = make_ref_shift_model(enc)
+    rec = {}
+    # 1. the survey's hand example and two more rows
+    ids = torch.tensor([[0, 0, 1, 5, 6, 0, 7, 8, 0, 9, 2, 3],
+                        [1, 4, 4, 4, 0, 6, 6, 6, 0, 7, 7, 2]])
+    rec["ids"] = ids.numpy()
+    for n in (1, 2):
+        rec[f"label_mask_sep{n}"] = model.generate_label_mask({"input_ids": ids}, n).numpy()
+    rec["label_mask_sep1_keep_bos"] = model.generate_label_mask({"input_ids": ids}, 1, keep_bos=True).numpy()
+    # 2. get_hidden_states + LAYER_WISE_MSE on ragged Nq_i
+    g = torch.Generator().manual_seed(3407)
+    L, B, S, D = 3, 2, 12, 64
+    ctx = [torch.randn(B, S, D, generator=g) for _ in range(L)]
+    mask_ctx = model.generate_label_mask({"input_ids": ids}, 1)          # 5 and 6 rows
+    enc.ffn_hidden_states = ctx
+    hp = model.get_hidden_states(mask_ctx)
+    T = 8
+    qry = [torch.randn(B, T, D, generator=g) for _ in range(L)]
+    mask_q = torch.zeros(B, T, dtype=torch.bool)
+    mask_q[0, T - int(mask_ctx[0].sum()):] = True
+    mask_q[1, T - int(mask_ctx[1].sum()):] = True
+    enc.ffn_hidden_states = [t.clone().requires_grad_(True) for t in qry]
+    hq = model.get_hidden_states(mask_q)
+    loss = model.calculate_layer_wise_loss(hq, hp)
+    assert list(loss.keys()) == ["ffn_mse_loss"]
+    grads = torch.autograd.grad(loss["ffn_mse_loss"], enc.ffn_hidden_states)
+    rec.update(ctx=torch.stack(ctx).numpy(), qry=torch.stack(qry).numpy(), mask_ctx=mask_ctx.numpy(),
+               mask_q=mask_q.numpy(), ffn_mse_loss=loss["ffn_mse_loss"].detach().numpy(),
+               dqry=torch.stack(grads).numpy(),
+               hp0=hp["ffn_hidden_states"][0].numpy(), hp1=hp["ffn_hidden_states"][1].numpy())
+    # 3. COS_SIM variant
+    model2, _ = make_ref_shift_model(enc, "Strategy.LAYER_WISE_COS_SIM")
+    rec["ffn_cos_sim"] = model2.calculate_layer_wise_loss(hq, hp)["ffn_cos_sim"].detach().numpy()
+    # 4. logits KL
+    a = torch.randn(7, 50, generator=g)
+    b = torch.randn(7, 50, generator=g)
+    m = torch.ones(7, dtype=torch.bool)
+    rec.update(kl_a=a.numpy(), kl_b=b.numpy(),
+               kl=model.calculate_logits_kl_loss(a, b, m, m)["logits_kl_loss"].numpy())
+    np.savez_compressed(os.path.join(OUT, "loss_pieces.npz"), **rec)
+    print("loss pieces: mse", float(rec["ffn_mse_loss"]), "cos", float(rec["ffn_cos_sim"]), "kl", float(rec["kl"]))
+
+
+# ---------------------------------------------------------------- tiny end-to-end step (BASELINE config 1)
+
+def build_tiny_ids(seed=3407, B=2, n_ctx=96, n_query=(20, 14), n_answer=(3, 5), vocab=512):
+    """[bos] ICE [PAD] query [PAD] answer [EOS], left-padded; and the query-only rows."""
+    g = torch.Generator().manual_seed(seed)
+    tok = _Tok()
+    full, qa = [], []
+    for i in range(B):
+        ice = torch.randint(3, vocab, (n_ctx - 3 * i,), generator=g).tolist()
+        query = torch.randint(3, vocab, (n_query[i],), generator=g).tolist()
+        ans = torch.randint(3, vocab, (n_answer[i],), generator=g).tolist()
+        full.append([tok.bos_token_id] + ice + [tok.pad_token_id] + query + [tok.pad_token_id] + ans + [tok.eos_token_id])
+        qa.append([tok.bos_token_id] + query + [tok.pad_token_id] + ans + [tok.eos_token_id])
+
+    def left_pad(rows):
+        n = max(len(r) for r in rows)
+        return torch.tensor([[tok.pad_token_id] * (n - len(r)) + r for r in rows])
+
+    return left_pad(full), left_pad(qa)
+
+
+def tiny_qwen2(seed=3407):
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    torch.manual_seed(seed)
+    cfg = Qwen2Config(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=4,
+                      num_attention_heads=8, num_key_value_heads=8, attn_implementation="sdpa",
+                      max_position_embeddings=1024)
+    cfg.text_config = cfg
+    cfg.use_sliding_window = False
+    lm = Qwen2ForCausalLM(cfg).float()
+    lm.requires_grad_(False)
+
+    class Wrap(torch.nn.Module):                       # names match language_model\.model\.layers\.\d+\.self_attn$
+        def __init__(self):
+            super().__init__()
+            self.language_model = lm
+            self.config = cfg
+
+        def forward(self, **kw):
+            return self.language_model(**kw)
+
+    return Wrap()
+
+
+def gen_tiny_step():
+    mb = ref_loader.load_model_base()
+    from torch import nn
+
+    class TinyLMM(mb.ModelBase):
+        def __init__(self, model):
+            nn.Module.__init__(self)
+            self.model = model
+            self.model_name = "llava-interleave-qwen-7b-hf"
+            self.config = model.config
+            self._trackers_dict = {}
+
+    lmm = TinyLMM(tiny_qwen2())
+    enc = ref_loader.make_ref_encoder(256, 4, 8, lmm=lmm)
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():                              # trained-like so the shift path matters
+        enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.05)
+        for lin in enc.log_Z1_lin:
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.1)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.5)
+    init = {k: v.detach().clone() for k, v in enc.state_dict().items() if not k.startswith("lmm")}
+    model, sm = make_ref_shift_model(enc)
+    full_ids, qa_ids = build_tiny_ids()
+    tok = _Tok()
+
+    # ---- ShiftModel.forward (src/shift_model.py:193-285) restated at token-id level; every
+    # ---- mask / hidden-state / loss call below is the imported reference method.
+    hooks = enc.register_record_hooks()
+    inputs = {"input_ids": full_ids, "attention_mask": full_ids != tok.pad_token_id}
+    q_inputs = {"input_ids": qa_ids, "attention_mask": qa_ids != tok.pad_token_id}
+    with torch.no_grad():
+        lmm.model(**inputs)
+    prefix_hs = model.get_hidden_states(model.generate_label_mask(inputs, 1))
+    hooks.update(enc.register_shift_hooks())
+    logits = lmm.model(**q_inputs)["logits"]
+    # LM loss, transformers==4.45.2 rule (oracle/losses.py::lm_ce_loss; parity unpinned there)
+    keep = q_inputs["attention_mask"][:, 1:]
+    ce = F.cross_entropy(logits[:, :-1][keep].float(), qa_ids[:, 1:][keep])
+    shift_hs = model.get_hidden_states(q_inputs["attention_mask"] & (qa_ids != tok.bos_token_id))
+    model.remove_hooks(hooks)
+    layer_loss = model.calculate_layer_wise_loss(shift_hs, prefix_hs)
+    loss = 0.5 * ce + 1.0 * sum(layer_loss.values())
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    grads = torch.autograd.grad(loss, list(params.values()))
+    rec = {"full_ids": full_ids.numpy(), "qa_ids": qa_ids.numpy(), "loss": loss.detach().numpy(),
+           "ce_loss": ce.detach().numpy(), "ffn_mse_loss": layer_loss["ffn_mse_loss"].detach().numpy(),
+           "logits_checksum": logits.detach().double().abs().sum().numpy(),
+           "weights_checksum": np.array(sum(float(p.double().abs().sum()) for p in lmm.model.parameters()))}
+    for (n, p), gr in zip(params.items(), grads):
+        rec["init." + n] = init[n].numpy()
+        rec["grad." + n] = gr.numpy()
+    # one AdamW step with the reference's two weight-decay groups (src/shift_model.py:306-372)
+    for (n, p), gr in zip(params.items(), grads):
+        p.grad = gr
+    torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)            # train.yaml grad_clip_val
+    opt = torch.optim.AdamW([
+        {"params": [p for n, p in params.items() if "bias" in n], "weight_decay": 0.0, "lr": 5e-3},
+        {"params": [p for n, p in params.items() if "bias" not in n], "weight_decay": 1e-3, "lr": 5e-3}],
+        weight_decay=1e-3)
+    opt.step()
+    for n, p in params.items():
+        rec["after." + n] = p.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_step.npz"), **rec)
+    print("tiny step: loss", float(loss), "ce", float(ce), "mse", float(layer_loss["ffn_mse_loss"]))
+
+
+def main():
+    assert ref_loader.available(), "reference tree not found; golden vectors can only be made where it is"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    gen_attention()
+    gen_loss_pieces()
+    gen_tiny_step()
+
+
+if __name__ == "__main__":
+    main()
