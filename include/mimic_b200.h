@@ -1,0 +1,160 @@
+/*
+ * mimic_b200.h — C ABI of the B200-native MimIC hot path.
+ *
+ * One shared library (libmimic_b200.so), plain C symbols, raw device pointers and sizes, no
+ * torch types.  Every entry point enqueues work on the caller's CUDA stream and returns an int
+ * status (0 = ok); `mimic_last_error()` gives the message of the last failure on this thread.
+ * Nothing here allocates device memory: scratch comes from a caller-provided workspace whose
+ * size the matching `*_workspace()` query returns.
+ *
+ * The reference (mercurystraw/MimIC) is pure Python and has no FFI of its own; each entry point
+ * below names the reference call sites (file:line, relative to the reference tree) it replaces.
+ * The binding a maintainer of the reference would add is shown in INTEGRATION.md.
+ */
+#ifndef MIMIC_B200_H_
+#define MIMIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMIC_ABI_VERSION 1
+#define MIMIC_API __attribute__((visibility("default")))
+
+enum { MIMIC_OK = 0, MIMIC_ERR_ARG = 1, MIMIC_ERR_CUDA = 2, MIMIC_ERR_UNSUPPORTED = 3 };
+
+/* storage type of activations; all statistics / parameter gradients are fp32 */
+enum { MIMIC_BF16 = 0, MIMIC_F32 = 1 };
+
+/* which implementation `mimic_shifted_attn_*` picks for bf16, d == 128 (both are CUDA):
+ * AUTO = tcgen05/TMA kernels when the shape allows, else the SIMT kernels. */
+enum { MIMIC_IMPL_AUTO = 0, MIMIC_IMPL_SIMT = 1, MIMIC_IMPL_TCGEN05 = 2 };
+
+MIMIC_API int mimic_abi_version(void);
+MIMIC_API const char* mimic_last_error(void);
+/* name of the kernel family the last mimic_shifted_attn_* call on this thread launched */
+MIMIC_API const char* mimic_last_attn_impl(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Shifted self-attention.
+ *
+ * Replaces, per decoder layer, F.scaled_dot_product_attention (src/shift_encoder.py:352-359,
+ * 449-456, 518-532) followed by AttnApproximator.do_shift (src/shift_encoder.py:682-732):
+ *
+ *   SA_t      = softmax_{s visible from t}(scale * q_t.k_s) . v_s
+ *   lse_full  = log sum_{ALL s in [0,S)} exp(scale * q_t.k_s)          (unmasked, lines 697-703)
+ *   z1_t      = q_t . w[h] + bias[h]                                    (MultiheadLinear, 547-556)
+ *   mu_t      = exp(z1_t - logaddexp(z1_t, lse_full))                   (line 712)
+ *   out_t     = SA_t + mu_t * shift[h]                                  (line 724)
+ *
+ * visible(b,t,s) = (!causal || s <= t + (S - T)) && (key_mask == NULL || key_mask[b*S+s] != 0).
+ * A query row with no visible key gets SA = 0.  `active == 0` is the inactive-handle path (line
+ * 685/732): out = SA, and lse_full / mu / shift / w / bias may be NULL.
+ *
+ * Layouts (element strides; the innermost, head_dim, stride is 1 for every tensor):
+ *   q   [B,H,T,d]    strides q_sb,q_sh,q_st      k,v [B,Hkv,S,d]  strides k_*, v_*   (H % Hkv == 0)
+ *   out [B,T,H,d]    strides o_sb,o_st,o_sh      (the layout do_shift returns)
+ *   lse_c, lse_full, mu : fp32 [B,H,T] contiguous.  shift, w: fp32 [H,d]; bias: fp32 [H].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t B, H, Hkv, T, S, d;
+  int64_t q_sb, q_sh, q_st;
+  int64_t k_sb, k_sh, k_ss;
+  int64_t v_sb, v_sh, v_ss;
+  int64_t o_sb, o_st, o_sh;
+  float scale;        /* 1/sqrt(d) in the reference (line 699) */
+  int32_t causal;
+  int32_t active;
+  int32_t dtype;      /* MIMIC_BF16 | MIMIC_F32 */
+  int32_t impl;       /* MIMIC_IMPL_* */
+} mimic_attn_desc_t;
+
+MIMIC_API int mimic_shifted_attn_fwd(const mimic_attn_desc_t* desc,
+                           const void* q, const void* k, const void* v,
+                           const uint8_t* key_mask,
+                           const float* shift, const float* w, const float* bias,
+                           void* out, float* lse_c, float* lse_full, float* mu,
+                           void* stream);
+
+/* Backward of the above (replaces the autograd graph of SDPA + do_shift).
+ *   d_out [B,T,H,d] with the strides of `out` in desc (go_* below override when non-zero).
+ *   dq [B,H,T,d], dk, dv [B,Hkv,S,d]: contiguous, dtype of desc, fully overwritten.
+ *   dshift, dw [H,d], dbias [H]: fp32, ACCUMULATED INTO (+=) — they point into the flat
+ *   parameter-gradient buffer that the data-parallel all-reduce later sums (src/config/train.yaml:14).
+ * workspace: mimic_shifted_attn_bwd_workspace(desc) bytes, 256-byte aligned. */
+MIMIC_API size_t mimic_shifted_attn_bwd_workspace(const mimic_attn_desc_t* desc);
+MIMIC_API int mimic_shifted_attn_bwd(const mimic_attn_desc_t* desc,
+                           const void* q, const void* k, const void* v,
+                           const uint8_t* key_mask,
+                           const float* shift, const float* w, const float* bias,
+                           const void* out, const void* d_out,
+                           int64_t go_sb, int64_t go_st, int64_t go_sh,
+                           const float* lse_c, const float* lse_full, const float* mu,
+                           void* dq, void* dk, void* dv,
+                           float* dshift, float* dw, float* dbias,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Record path: gather the selected token rows of one layer's recorded module output straight
+ * into the preallocated [L, N, D] buffer.  Replaces record_hook (src/shift_encoder.py:115-120)
+ * + torch.stack + masked_select in ShiftModel.get_hidden_states (src/shift_model.py:131-136).
+ *   src [rows, D] (row stride src_row_stride elements), src_row[n] = source row of compact row n.
+ *   dst [N, D] contiguous (the layer's slice), dst_dtype may differ from src_dtype.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_record_gather(const void* src, int64_t src_row_stride, int32_t src_dtype,
+                        const int32_t* src_row, void* dst, int32_t dst_dtype,
+                        int32_t N, int32_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layer-wise alignment loss, Strategy.LAYER_WISE_MSE, forward + backward in one pass.
+ * Replaces ShiftModel.calculate_layer_wise_loss (src/shift_model.py:145-179) and its autograd:
+ *   loss = mean_i mean_{l,t,d} (H_i - H'_i)^2 = sum_{l,n,d} row_w[n] * (H[l][row[n]] - H'[l][n])^2
+ * with row_w[n] = 1 / (n_samples * L * Nq_{sample(n)} * D) supplied by the caller.
+ *   h_ptrs   device array of L pointers; layer l's query-pass module output [rows, D], h_row_stride
+ *   hp       H' compact [L, N, D] (written by mimic_record_gather), hp_dtype
+ *   row_to_compact [rows]: compact index n of row r, or -1 when the row is not selected
+ *   dh_ptrs  device array of L pointers to [rows, D] contiguous gradients in h dtype, fully
+ *            written (zeros on unselected rows): dH = grad_scale * 2 * row_w * (H - H').
+ *            NULL = forward only.
+ *   loss     fp32 [1], overwritten.   partial: fp32 workspace of mimic_mse_workspace() bytes.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API size_t mimic_mse_workspace(int32_t L, int32_t rows, int32_t D);
+MIMIC_API int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype,
+                      const void* hp, int32_t hp_dtype,
+                      const int32_t* row_to_compact, const float* row_w,
+                      void* const* dh_ptrs, float grad_scale,
+                      int32_t L, int32_t rows, int32_t N, int32_t D,
+                      float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LM-loss cross-entropy, forward + backward in one launch, gradient optionally in place.
+ * Replaces the HF in-model loss invoked at src/shift_model.py:238-250 (log_softmax + nll_loss on
+ * fp32-upcast logits, mean over kept positions).
+ *   logits [R, V] (row stride logits_row_stride), labels int64 [R]; label < 0 = ignored row.
+ *   dlogits [R, V] contiguous-or-same-stride as logits (may alias logits); NULL = forward only:
+ *            dlogits = grad_scale * (softmax(logits) - onehot(label)) / n_kept, 0 on ignored rows.
+ *   loss fp32 [1] overwritten with the mean over kept rows (0 when none); n_kept int32 [1].
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, int32_t dtype,
+                     const int64_t* labels, void* dlogits, float grad_scale,
+                     int32_t R, int32_t V, float* loss, int32_t* n_kept, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * On-device optimizer step for the flat fp32 shift-parameter buffer: global-norm clip
+ * (train.yaml grad_clip_val) + AdamW with per-element weight decay (the reference's two groups,
+ * src/shift_model.py:306-372: names containing "bias" get 0).  Replaces DeepSpeedCPUAdam's host
+ * round trip.  lr arrives as a device scalar so a captured graph can replay it.
+ *   sumsq: fp32 [1] workspace.  grad is scaled in place by grad_mul (1/world, 1/accum) first.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                     const float* weight_decay, int64_t n, const float* lr, float beta1, float beta2,
+                     float eps, int32_t step, float grad_mul, float max_norm, float* sumsq,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMIC_B200_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of libmimic_b200.so (include/mimic_b200.h).  There is NO fallback: if the
+library cannot be loaded (and cannot be built because nvcc is absent) importing this module
+raises, and every op raises `MimicError` on a non-zero status."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmimic_b200.so")
+
+BF16, F32 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tcgen05": IMPL_TCGEN05}
+
+
+class MimicError(RuntimeError):
+    pass
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "Hkv", "T", "S", "d")] + \
+               [(n, C.c_int64) for n in ("q_sb", "q_sh", "q_st", "k_sb", "k_sh", "k_ss",
+                                         "v_sb", "v_sh", "v_ss", "o_sb", "o_st", "o_sh")] + \
+               [("scale", C.c_float), ("causal", C.c_int32), ("active", C.c_int32),
+                ("dtype", C.c_int32), ("impl", C.c_int32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "mimic_abi_version": (C.c_int, []),
+    "mimic_last_error": (C.c_char_p, []),
+    "mimic_last_attn_impl": (C.c_char_p, []),
+    "mimic_shifted_attn_fwd": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 12),
+    "mimic_shifted_attn_bwd_workspace": (C.c_size_t, [C.POINTER(AttnDesc)]),
+    "mimic_shifted_attn_bwd": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 9 + [C.c_int64] * 3 +
+                               [C.c_void_p] * 10 + [C.c_size_t, C.c_void_p]),
+    "mimic_record_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
+    "mimic_mse_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "mimic_mse_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mimic_ce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mimic_adamw_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                                     C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+}
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build   # needs nvcc; raises when it is missing
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)       # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mimic_abi_version() != 1:
+        raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 1; rebuild (python -m mimic_b200.build --force)")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise MimicError(f"{what} failed (status {rc}): {lib.mimic_last_error().decode()}")
+
+
+def last_attn_impl() -> str:
+    return lib.mimic_last_attn_impl().decode()

@@ -1,0 +1,40 @@
+// Parameter block shared by the shifted-attention kernel families.
+#pragma once
+#include "common.cuh"
+
+namespace mimic {
+
+struct AttnParams {
+  int B, H, Hkv, T, S, d;
+  int64_t q_sb, q_sh, q_st;
+  int64_t k_sb, k_sh, k_ss;
+  int64_t v_sb, v_sh, v_ss;
+  int64_t o_sb, o_st, o_sh;
+  int64_t go_sb, go_st, go_sh;
+  float scale;
+  int causal, active, dtype;
+  const void *q, *k, *v;
+  const uint8_t* key_mask;
+  const float *shift, *w, *bias;
+  void* out;
+  float *lse_c, *lse_full, *mu;
+  // backward only
+  const void* d_out;
+  void *dq, *dk, *dv;
+  float *dshift, *dw, *dbias;
+  float *dq_acc, *delta_ws, *dz_ws;
+};
+
+namespace simt {
+int fwd(const AttnParams& p, cudaStream_t st);
+int bwd(const AttnParams& p, cudaStream_t st);
+}  // namespace simt
+
+namespace tc {
+// tcgen05 / TMEM / TMA kernels: bf16, d == 128
+bool supports(const AttnParams& p, bool backward);
+int fwd(const AttnParams& p, cudaStream_t st);
+int bwd(const AttnParams& p, cudaStream_t st);
+}  // namespace tc
+
+}  // namespace mimic

@@ -1,0 +1,405 @@
+// HBM-bound kernels of the MimIC hot path: record gather (R), fused layer-wise MSE forward+backward
+// (M), fused LM-loss cross-entropy forward+backward (C), and the on-device clip + AdamW step.
+// All are single launches over all layers / rows, 16-byte vectorised, streaming (L1 no-allocate)
+// loads and stores, persistent grid-stride over rows with grids sized from the SM count.
+#include "common.cuh"
+
+namespace mimic {
+
+// ---------------------------------------------------------------------------------------------
+// 8-element chunk I/O with streaming hints
+template <typename T>
+struct Chunk;
+template <>
+struct Chunk<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 u = ldg_stream(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    stg_stream(p, u);
+  }
+};
+template <>
+struct Chunk<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    uint4 a = ldg_stream(p), b = ldg_stream(p + 4);
+    f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+    f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+    stg_stream(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+    stg_stream(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+  }
+};
+
+__device__ __forceinline__ float block_sum(float v, float* sh /*[32]*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (warp == 0) v = warp_sum(v);
+  return v;  // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// R: record gather
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) record_gather_kernel(const TS* __restrict__ src, int64_t src_row_stride,
+                                                            const int32_t* __restrict__ src_row,
+                                                            TD* __restrict__ dst, int N, int D) {
+  const int chunks = D / 8;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const int sr = src_row[n];           // -1 = unused slot of the fixed-capacity buffer: zero it
+    const TS* s = src + (int64_t)(sr < 0 ? 0 : sr) * src_row_stride;
+    TD* d = dst + (int64_t)n * D;
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (sr >= 0) Chunk<TS>::load(s + c * 8, f);
+      Chunk<TD>::store(d + c * 8, f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// M: fused layer-wise MSE forward + backward.  Work item = one (layer, row); a CTA walks items
+// grid-stride; per item each thread moves 8-element chunks of H, H' and dH.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
+                                                          const T* __restrict__ hp,
+                                                          const int32_t* __restrict__ row_to_compact,
+                                                          const float* __restrict__ row_w,
+                                                          void* const* __restrict__ dh_ptrs, float grad_scale, int L,
+                                                          int rows, int N, int D, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const int chunks = D / 8;
+  const int64_t items = (int64_t)L * rows;
+  float acc = 0.f;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int l = (int)(it / rows), r = (int)(it % rows);
+    const int c = row_to_compact[r];
+    T* dh = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) + (int64_t)r * D : nullptr;
+    if (c < 0) {
+      if (dh) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) Chunk<T>::store(dh + ch * 8, z);
+      }
+      continue;
+    }
+    const T* h = reinterpret_cast<const T*>(h_ptrs[l]) + (int64_t)r * h_row_stride;
+    const T* t = hp + ((int64_t)l * N + c) * D;
+    const float w = row_w[c];
+    const float gw = 2.f * w * grad_scale;
+    for (int ch0 = threadIdx.x; ch0 < chunks; ch0 += blockDim.x * UNROLL) {
+      float a[UNROLL][8], b[UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int ch = ch0 + u * blockDim.x;
+        if (ch < chunks) {
+          Chunk<T>::load(h + ch * 8, a[u]);
+          Chunk<T>::load(t + ch * 8, b[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int ch = ch0 + u * blockDim.x;
+        if (ch < chunks) {
+          float g[8];
+          float s = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float df = a[u][e] - b[u][e];
+            s += df * df;
+            g[e] = gw * df;
+          }
+          acc += w * s;
+          if (dh) Chunk<T>::store(dh + ch * 8, g);
+        }
+      }
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
+static int mse_grid(int L, int rows) {
+  const int64_t items = (int64_t)L * rows;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (int)(items < cap ? items : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C: fused cross-entropy forward + backward, one CTA per row (grid-stride).  Pass 1 reads the row
+// once from HBM keeping an online (max, sum); pass 2 re-reads it (L2-resident: the same CTA read
+// it microseconds earlier) and writes the gradient.  Rows need not be 16-byte aligned (V = 32003):
+// a scalar head/tail brackets the vector body.
+template <typename T>
+__device__ __forceinline__ int head_elems(const T* p, int V) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  constexpr uintptr_t AL = (sizeof(T) == 2) ? 16 : 32;   // one 8-element chunk
+  int h = (int)(((AL - (a % AL)) % AL) / sizeof(T));
+  return h < V ? h : V;
+}
+
+__device__ __forceinline__ void online_add(float& m, float& s, float x) {
+  if (x > m) {
+    s = s * __expf(m - x) + 1.f;
+    m = x;
+  } else {
+    s += __expf(x - m);
+  }
+}
+
+__global__ void ce_count_kernel(const int64_t* __restrict__ labels, int R, int32_t* __restrict__ n_kept, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) c += labels[i] >= 0 ? 1.f : 0.f;
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    n_kept[0] = (int32_t)(c + 0.5f);
+    loss[0] = 0.f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ logits, int64_t row_stride,
+                                                         const int64_t* __restrict__ labels, T* dlogits,
+                                                         float grad_scale, int R, int V,
+                                                         const int32_t* __restrict__ n_kept, float* __restrict__ loss) {
+  __shared__ float red[32];
+  __shared__ float bc[2];
+  const float inv_n = n_kept[0] > 0 ? 1.f / (float)n_kept[0] : 0.f;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const T* x = logits + (int64_t)r * row_stride;
+    T* dx = dlogits ? dlogits + (int64_t)r * row_stride : nullptr;
+    const int64_t label = labels[r];
+    const int head = head_elems(x, V);
+    const int body = (V - head) / 8;
+    const int tail0 = head + body * 8;
+    if (label < 0) {
+      if (dx) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = threadIdx.x; i < head; i += blockDim.x) dx[i] = from_f32<T>(0.f);
+        for (int c = threadIdx.x; c < body; c += blockDim.x) Chunk<T>::store(dx + head + c * 8, z);
+        for (int i = tail0 + threadIdx.x; i < V; i += blockDim.x) dx[i] = from_f32<T>(0.f);
+      }
+      continue;
+    }
+    // pass 1: online max / sum
+    float m = -INFINITY, s = 0.f;
+    for (int i = threadIdx.x; i < head; i += blockDim.x) online_add(m, s, to_f32(x[i]));
+    for (int c = threadIdx.x; c < body; c += blockDim.x) {
+      float f[8];
+      load8(x + head + c * 8, f);     // default caching: pass 2 wants these lines back
+      float cm = f[0];
+#pragma unroll
+      for (int e = 1; e < 8; ++e) cm = fmaxf(cm, f[e]);
+      if (cm > m) {
+        s *= __expf(m - cm);
+        m = cm;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += __expf(f[e] - m);
+    }
+    for (int i = tail0 + threadIdx.x; i < V; i += blockDim.x) online_add(m, s, to_f32(x[i]));
+    // block combine of (m, s)
+    float gm = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    gm = red[0];
+    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) gm = fmaxf(gm, red[wi]);
+    float ss = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+      bc[0] = gm;
+      bc[1] = ss;
+    }
+    __syncthreads();
+    gm = bc[0];
+    const float lse = gm + __logf(bc[1]);
+    const float inv_sum = 1.f / bc[1];
+    if (threadIdx.x == 0) atomicAdd(loss, (lse - to_f32(x[label])) * inv_n);
+    if (dx) {
+      const float gs = grad_scale * inv_n;
+      // pass 2: gradient.  x may alias dx: every element is read before it is written by the
+      // same thread, and no other thread touches it.
+      for (int i = threadIdx.x; i < head; i += blockDim.x) {
+        float pv = __expf(to_f32(x[i]) - gm) * inv_sum;
+        dx[i] = from_f32<T>(gs * (pv - (i == label ? 1.f : 0.f)));
+      }
+      for (int c = threadIdx.x; c < body; c += blockDim.x) {
+        float f[8];
+        const int base = head + c * 8;
+        load8(x + base, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = gs * (__expf(f[e] - gm) * inv_sum - ((base + e) == label ? 1.f : 0.f));
+        Chunk<T>::store(dx + base, f);
+      }
+      for (int i = tail0 + threadIdx.x; i < V; i += blockDim.x) {
+        float pv = __expf(to_f32(x[i]) - gm) * inv_sum;
+        dx[i] = from_f32<T>(gs * (pv - (i == label ? 1.f : 0.f)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip + AdamW on the flat fp32 parameter buffer
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ grad, int64_t n, float grad_mul, float* __restrict__ sumsq) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = grad[i] * grad_mul;
+    grad[i] = g;
+    acc += g * g;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(sumsq, acc);
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                                    float* __restrict__ v, const float* __restrict__ wd, int64_t n,
+                                                    const float* __restrict__ lr_p, float beta1, float beta2, float eps,
+                                                    float bc1, float bc2_sqrt, float max_norm, const float* __restrict__ sumsq) {
+  const float lr = lr_p[0];
+  float clip = 1.f;
+  if (max_norm > 0.f) {
+    const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);   // torch.nn.utils.clip_grad_norm_
+    clip = c < 1.f ? c : 1.f;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = grad[i] * clip;
+    float p = param[i];
+    p *= 1.f - lr * wd[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param[i] = p - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace mimic
+
+using namespace mimic;
+
+extern "C" int mimic_record_gather(const void* src, int64_t src_row_stride, int32_t src_dtype, const int32_t* src_row,
+                                   void* dst, int32_t dst_dtype, int32_t N, int32_t D, void* stream) {
+  MIMIC_CHECK_ARG(src && src_row && dst, "NULL argument");
+  MIMIC_CHECK_ARG(N >= 0 && D > 0 && D % 8 == 0 && src_row_stride % 8 == 0, "D and row stride must be multiples of 8");
+  if (N == 0) return MIMIC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = N < num_sms() * 8 ? N : num_sms() * 8;
+  if (src_dtype == MIMIC_BF16 && dst_dtype == MIMIC_BF16)
+    record_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)src, src_row_stride, src_row, (__nv_bfloat16*)dst, N, D);
+  else if (src_dtype == MIMIC_F32 && dst_dtype == MIMIC_F32)
+    record_gather_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, src_row_stride, src_row, (float*)dst, N, D);
+  else if (src_dtype == MIMIC_F32 && dst_dtype == MIMIC_BF16)
+    record_gather_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, src_row_stride, src_row,
+                                                                    (__nv_bfloat16*)dst, N, D);
+  else {
+    set_error("record_gather: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("record_gather_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" size_t mimic_mse_workspace(int32_t L, int32_t rows, int32_t D) {
+  (void)D;
+  return (size_t)(mse_grid(L, rows) + 1) * sizeof(float);
+}
+
+extern "C" int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype, const void* hp,
+                                 int32_t hp_dtype, const int32_t* row_to_compact, const float* row_w,
+                                 void* const* dh_ptrs, float grad_scale, int32_t L, int32_t rows, int32_t N,
+                                 int32_t D, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  MIMIC_CHECK_ARG(h_ptrs && hp && row_to_compact && row_w && loss && workspace, "NULL argument");
+  MIMIC_CHECK_ARG(L > 0 && rows > 0 && N >= 0 && D > 0 && D % 8 == 0 && h_row_stride % 8 == 0, "bad shape");
+  MIMIC_CHECK_ARG(h_dtype == hp_dtype, "H and H' must have the same storage type (got %d, %d)", h_dtype, hp_dtype);
+  MIMIC_CHECK_ARG(workspace_bytes >= mimic_mse_workspace(L, rows, D), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = mse_grid(L, rows);
+  float* partial = static_cast<float*>(workspace);
+  if (h_dtype == MIMIC_BF16)
+    mse_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial);
+  else if (h_dtype == MIMIC_F32)
+    mse_fwd_bwd_kernel<float, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w,
+                                                       dh_ptrs, grad_scale, L, rows, N, D, partial);
+  else {
+    set_error("mse: unsupported dtype %d", h_dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("mse_fwd_bwd_kernel");
+  sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, loss);
+  MIMIC_LAUNCH_OK("sum_partials_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, int32_t dtype, const int64_t* labels,
+                                void* dlogits, float grad_scale, int32_t R, int32_t V, float* loss, int32_t* n_kept,
+                                void* stream) {
+  MIMIC_CHECK_ARG(logits && labels && loss && n_kept, "NULL argument");
+  MIMIC_CHECK_ARG(R > 0 && V > 0 && logits_row_stride >= V, "bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ce_count_kernel<<<1, 256, 0, st>>>(labels, R, n_kept, loss);
+  MIMIC_LAUNCH_OK("ce_count_kernel");
+  const int grid = R < num_sms() * 4 ? R : num_sms() * 4;
+  if (dtype == MIMIC_BF16)
+    ce_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)logits, logits_row_stride, labels,
+                                                           (__nv_bfloat16*)dlogits, grad_scale, R, V, n_kept, loss);
+  else if (dtype == MIMIC_F32)
+    ce_fwd_bwd_kernel<float><<<grid, 512, 0, st>>>((const float*)logits, logits_row_stride, labels, (float*)dlogits,
+                                                   grad_scale, R, V, n_kept, loss);
+  else {
+    set_error("ce: unsupported dtype %d", dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("ce_fwd_bwd_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* weight_decay,
+                                int64_t n, const float* lr, float beta1, float beta2, float eps, int32_t step,
+                                float grad_mul, float max_norm, float* sumsq, void* stream) {
+  MIMIC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && weight_decay && lr && sumsq, "NULL argument");
+  MIMIC_CHECK_ARG(n > 0 && step >= 1, "bad n/step");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MIMIC_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(float), st));
+  const int grid = (int)((n + 255) / 256 < (int64_t)num_sms() * 4 ? (n + 255) / 256 : (int64_t)num_sms() * 4);
+  grad_sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_mul, sumsq);
+  MIMIC_LAUNCH_OK("grad_sumsq_kernel");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, weight_decay, n, lr, beta1, beta2, eps, bc1,
+                                     bc2_sqrt, max_norm, sumsq);
+  MIMIC_LAUNCH_OK("adamw_kernel");
+  return MIMIC_OK;
+}

@@ -1,0 +1,276 @@
+"""torch.autograd front-ends over the C ABI (include/mimic_b200.h).  PyTorch is plumbing here:
+device memory, the current stream, autograd bookkeeping.  All arithmetic is in libmimic_b200.so;
+there is no eager / CPU fallback — CPU tensors raise."""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, MimicError, check, lib
+
+_DT = {torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+
+# launch counter: every kernel family launch made through this module (bench.py reports it)
+launch_count = 0
+
+
+def _count(n: int) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MimicError("mimic_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _rows_ok(t: torch.Tensor) -> torch.Tensor:
+    """last dim contiguous, other strides multiples of 8 elements, 16-byte aligned base"""
+    if t.stride(-1) != 1 or any(s % 8 for s in t.stride()[:-1]) or t.data_ptr() % 16:
+        return t.contiguous()
+    return t
+
+
+def _make_desc(q, k, v, out, scale, causal, active, impl) -> AttnDesc:
+    B, H, T, d = q.shape
+    Hkv, S = k.shape[1], k.shape[2]
+    return AttnDesc(B=B, H=H, Hkv=Hkv, T=T, S=S, d=d,
+                    q_sb=q.stride(0), q_sh=q.stride(1), q_st=q.stride(2),
+                    k_sb=k.stride(0), k_sh=k.stride(1), k_ss=k.stride(2),
+                    v_sb=v.stride(0), v_sh=v.stride(1), v_ss=v.stride(2),
+                    o_sb=out.stride(0), o_st=out.stride(1), o_sh=out.stride(2),
+                    scale=float(scale), causal=int(bool(causal)), active=int(bool(active)),
+                    dtype=_DT[q.dtype], impl=_lib.IMPL_BY_NAME[impl])
+
+
+def shifted_attention_forward(q, k, v, key_mask, shift, w, bias, *, causal, active, scale, impl="auto"):
+    """Raw forward: returns (out [B,T,H,d], lse_c, lse_full, mu) with no autograd."""
+    _require_cuda(q, k, v, key_mask, shift, w, bias)
+    if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise MimicError(f"q/k/v must share dtype bf16 or fp32 (got {q.dtype}, {k.dtype}, {v.dtype})")
+    q, k, v = _rows_ok(q), _rows_ok(k), _rows_ok(v)
+    B, H, T, d = q.shape
+    out = torch.empty(B, T, H, d, dtype=q.dtype, device=q.device)
+    lse_c = torch.empty(B, H, T, dtype=torch.float32, device=q.device)
+    lse_full = torch.empty_like(lse_c) if active else None
+    mu = torch.empty_like(lse_c) if active else None
+    if key_mask is not None:
+        key_mask = key_mask.to(torch.uint8).contiguous()
+        if key_mask.shape != (B, k.shape[2]):
+            raise MimicError(f"key_mask must be [B,S]={B, k.shape[2]}, got {tuple(key_mask.shape)}")
+    if active:
+        shift, w, bias = (t.float().contiguous() for t in (shift, w, bias))
+    desc = _make_desc(q, k, v, out, scale, causal, active, impl)
+    check(lib.mimic_shifted_attn_fwd(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w),
+                                     _ptr(bias), _ptr(out), _ptr(lse_c), _ptr(lse_full), _ptr(mu), _stream()),
+          "mimic_shifted_attn_fwd")
+    _count(1)
+    return out, lse_c, lse_full, mu, (q, k, v, key_mask, shift, w, bias)
+
+
+def shifted_attention_backward(saved, out, d_out, lse_c, lse_full, mu, *, causal, active, scale, impl="auto",
+                               dshift=None, dw=None, dbias=None):
+    """Raw backward.  dshift/dw/dbias (fp32) are ACCUMULATED INTO when given, else allocated zeroed."""
+    q, k, v, key_mask, shift, w, bias = saved
+    B, H, T, d = q.shape
+    if d_out.stride(-1) != 1 or any(s % 8 for s in d_out.stride()[:-1]) or d_out.data_ptr() % 16:
+        d_out = d_out.contiguous()
+    dq = torch.empty(B, H, T, d, dtype=q.dtype, device=q.device)
+    dk = torch.empty(k.shape, dtype=q.dtype, device=q.device)
+    dv = torch.empty(v.shape, dtype=q.dtype, device=q.device)
+    if active:
+        if dshift is None:
+            dshift = torch.zeros(H, d, dtype=torch.float32, device=q.device)
+            dw = torch.zeros(H, d, dtype=torch.float32, device=q.device)
+            dbias = torch.zeros(H, dtype=torch.float32, device=q.device)
+    desc = _make_desc(q, k, v, out, scale, causal, active, impl)
+    nbytes = lib.mimic_shifted_attn_bwd_workspace(desc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    check(lib.mimic_shifted_attn_bwd(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w), _ptr(bias),
+                                     _ptr(out), _ptr(d_out), d_out.stride(0), d_out.stride(1), d_out.stride(2),
+                                     _ptr(lse_c), _ptr(lse_full), _ptr(mu), _ptr(dq), _ptr(dk), _ptr(dv),
+                                     _ptr(dshift), _ptr(dw), _ptr(dbias), _ptr(ws), nbytes, _stream()),
+          "mimic_shifted_attn_bwd")
+    _count(3)
+    return dq, dk, dv, dshift, dw, dbias
+
+
+class GradSink:
+    """Views into the flat fp32 parameter-gradient buffer for one layer: the attention backward
+    accumulates straight into them (no per-layer temporaries, one all-reduce over the flat buffer)."""
+
+    def __init__(self, dshift: torch.Tensor, dw: torch.Tensor, dbias: torch.Tensor):
+        self.dshift, self.dw, self.dbias = dshift, dw, dbias
+
+
+class _ShiftedAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, shift, w, bias, key_mask, causal, active, scale, impl, sink):
+        out, lse_c, lse_full, mu, saved = shifted_attention_forward(
+            q, k, v, key_mask, shift, w, bias, causal=causal, active=active, scale=scale, impl=impl)
+        ctx.saved = saved
+        ctx.stats = (out, lse_c, lse_full, mu)
+        ctx.cfg = (causal, active, scale, impl)
+        ctx.sink = sink
+        ctx.param_dtypes = tuple(None if t is None else t.dtype for t in (shift, w, bias))
+        ctx.mark_non_differentiable(lse_c)
+        return out, lse_c
+
+    @staticmethod
+    def backward(ctx, d_out, _d_lse):
+        causal, active, scale, impl = ctx.cfg
+        out, lse_c, lse_full, mu = ctx.stats
+        sink = ctx.sink
+        dq, dk, dv, dshift, dw, dbias = shifted_attention_backward(
+            ctx.saved, out, d_out, lse_c, lse_full, mu, causal=causal, active=active, scale=scale, impl=impl,
+            dshift=None if sink is None else sink.dshift, dw=None if sink is None else sink.dw,
+            dbias=None if sink is None else sink.dbias)
+        if sink is not None or not active:
+            dshift = dw = dbias = None
+        else:
+            dshift, dw, dbias = (g.to(dt) for g, dt in zip((dshift, dw, dbias), ctx.param_dtypes))
+        return dq, dk, dv, dshift, dw, dbias, None, None, None, None, None, None
+
+
+def shifted_attention(q, k, v, shift=None, w=None, bias=None, key_mask=None, *, causal=True, active=True,
+                      scale=None, impl="auto", grad_sink: Optional[GradSink] = None, return_lse=False):
+    """out[B,T,H,d] = SDPA(q,k,v) + mu(q,k) * shift   — the fused replacement of
+    F.scaled_dot_product_attention + AttnApproximator.do_shift (src/shift_encoder.py:352-359, 682-732).
+
+    q [B,H,T,d], k/v [B,Hkv,S,d], shift/w [H,d], bias [H], key_mask [B,S] (True/1 = attend)."""
+    if scale is None:
+        scale = 1.0 / math.sqrt(q.shape[-1])
+    out, lse_c = _ShiftedAttention.apply(q, k, v, shift, w, bias, key_mask, causal, active, scale, impl, grad_sink)
+    return (out, lse_c) if return_lse else out
+
+
+# ------------------------------------------------------------------------------------------------
+def record_gather(src: torch.Tensor, src_row: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[n,:] = src.view(-1,D)[src_row[n],:]   (kernel R; src_row int32 on device)."""
+    _require_cuda(src, src_row, dst)
+    D = src.shape[-1]
+    src2 = src.reshape(-1, D)
+    if src2.stride(1) != 1:
+        src2 = src2.contiguous()
+    N = src_row.numel()
+    assert dst.shape == (N, D) and dst.is_contiguous() and src_row.dtype == torch.int32
+    check(lib.mimic_record_gather(_ptr(src2), src2.stride(0), _DT[src2.dtype], _ptr(src_row), _ptr(dst), _DT[dst.dtype],
+                                  N, D, _stream()), "mimic_record_gather")
+    _count(1)
+
+
+class _AlignMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hp, row_to_compact, row_w, grad_scale, assume_folded, *hs):
+        L = len(hs)
+        h0 = hs[0]
+        D = h0.shape[-1]
+        rows = h0.numel() // D
+        hs = [h if (h.is_contiguous()) else h.contiguous() for h in hs]
+        N = hp.shape[1]
+        dev = h0.device
+        need_grad = any(ctx.needs_input_grad[5:])
+        ptrs = [h.data_ptr() for h in hs]
+        dh = torch.empty((L, rows, D), dtype=h0.dtype, device=dev) if need_grad else None
+        if need_grad:
+            step = rows * D * dh.element_size()
+            ptrs += [dh.data_ptr() + l * step for l in range(L)]
+        ptr_t = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=True)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        nbytes = lib.mimic_mse_workspace(L, rows, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.mimic_mse_fwd_bwd(ptr_t.data_ptr(), D, _DT[h0.dtype], _ptr(hp), _DT[hp.dtype], _ptr(row_to_compact),
+                                    _ptr(row_w), (ptr_t.data_ptr() + 8 * L) if need_grad else None, float(grad_scale),
+                                    L, rows, N, D, _ptr(loss), _ptr(ws), nbytes, _stream()), "mimic_mse_fwd_bwd")
+        _count(2)
+        ctx.dh = dh
+        ctx.shapes = [h.shape for h in hs]
+        ctx.grad_scale = grad_scale
+        ctx.assume_folded = assume_folded
+        ctx.keepalive = (ptr_t, hs)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dh = ctx.dh
+        if dh is None:
+            return (None,) * (5 + len(ctx.shapes))
+        if not ctx.assume_folded:
+            dh = dh * (g / ctx.grad_scale).to(dh.dtype)
+        return (None, None, None, None, None) + tuple(dh[l].view(s) for l, s in enumerate(ctx.shapes))
+
+
+def align_mse(hs: Sequence[torch.Tensor], hp: torch.Tensor, row_to_compact: torch.Tensor, row_w: torch.Tensor,
+              grad_scale: float = 1.0, assume_folded: bool = False) -> torch.Tensor:
+    """Layer-wise MSE (src/shift_model.py:145-179) over L recorded tensors [*, D] against the compact
+    H' buffer [L,N,D]; one fused forward+backward launch.  With `assume_folded`, the caller promises
+    the upstream gradient of the returned scalar is exactly `grad_scale` (it was folded into dH)."""
+    _require_cuda(hp, row_to_compact, row_w, *hs)
+    return _AlignMSE.apply(hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
+
+
+class _CELoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, grad_scale, assume_folded, inplace):
+        V = logits.shape[-1]
+        lg = logits.reshape(-1, V)
+        if lg.stride(1) != 1:
+            lg = lg.contiguous()
+        R = lg.shape[0]
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        dev = lg.device
+        need_grad = ctx.needs_input_grad[0]
+        dlog = None
+        if need_grad:
+            dlog = lg if inplace else torch.empty_like(lg)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        n_kept = torch.empty(1, dtype=torch.int32, device=dev)
+        check(lib.mimic_ce_fwd_bwd(_ptr(lg), lg.stride(0), _DT[lg.dtype], _ptr(labels), _ptr(dlog), float(grad_scale),
+                                   R, V, _ptr(loss), _ptr(n_kept), _stream()), "mimic_ce_fwd_bwd")
+        _count(2)
+        ctx.dlog = dlog
+        ctx.shape = logits.shape
+        ctx.grad_scale = grad_scale
+        ctx.assume_folded = assume_folded
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.dlog
+        if d is None:
+            return None, None, None, None, None
+        if not ctx.assume_folded:
+            d = d * (g / ctx.grad_scale).to(d.dtype)
+        return d.view(ctx.shape), None, None, None, None
+
+
+def ce_loss(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, assume_folded: bool = False,
+            inplace: bool = False) -> torch.Tensor:
+    """Mean CE over rows with label >= 0 (fp32 math), forward+backward in one launch.
+    logits [..., V] (bf16/fp32), labels [...] int64 (-100 = ignore)."""
+    _require_cuda(logits, labels)
+    return _CELoss.apply(logits, labels, grad_scale, assume_folded, inplace)
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, lr: torch.Tensor, step: int, *, betas=(0.9, 0.999),
+               eps=1e-8, grad_mul=1.0, max_norm=0.0, sumsq: Optional[torch.Tensor] = None) -> None:
+    """Clip (global norm) + AdamW on flat fp32 buffers, on device (replaces DeepSpeedCPUAdam)."""
+    _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, lr)
+    if sumsq is None:
+        sumsq = torch.empty(1, dtype=torch.float32, device=param.device)
+    check(lib.mimic_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(weight_decay),
+                               param.numel(), _ptr(lr), betas[0], betas[1], eps, int(step), float(grad_mul),
+                               float(max_norm), _ptr(sumsq), _stream()), "mimic_adamw_step")
+    _count(2)

@@ -1,0 +1,355 @@
+"""Drop-in mirror of the reference's shift encoders (src/shift_encoder.py) with the arithmetic moved
+into hand-written sm_100a CUDA behind the C ABI.
+
+Same names, constructor arguments, hook methods, handle objects and state-dict keys as the
+reference (`AttnApproximator`, `BaseHookEncoder`, `ShiftStrategy`, `AttnApproxHandle`,
+`MultiheadLinear`; keys `attn_shift`, `log_Z1_lin.{l}.weight/bias`), so `encoder.pth` files load
+both ways.  What changed underneath:
+
+  * the replaced attention forward calls ONE fused op, `ops.shifted_attention`, instead of
+    SDPA (shift_encoder.py:352-359 / 449-456 / 518-532) followed by `do_shift` (682-732);
+  * `do_shift` itself is kept for API parity and runs the same fused kernel on caller-made
+    attention output (it recomputes nothing on the host);
+  * record hooks can gather the selected token rows straight into a preallocated buffer
+    (`RecordPlan`, kernel R) instead of keeping L full activations alive (113-140).
+"""
+from __future__ import annotations
+
+import enum
+import inspect
+import re
+from functools import partial
+from typing import Callable, Dict, List, Optional, Union
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class HookType(enum.Enum):
+    TEXT_MODEL_LAYER = enum.auto()
+    VISION_MODEL_LAYER = enum.auto()
+
+
+class ShiftStrategy(enum.IntFlag):       # values are API: src/shift_encoder.py:15-19
+    VECTOR_SHIFT = 1
+    RECORD_HIDDEN_STATES = 4
+    LEARNABLE_SHIFT_SCALE = 8
+    MULTI_HEAD = 16
+
+
+def parse_strategy_flags(value, enum_cls=ShiftStrategy):
+    """The reference `eval`s strategy strings like "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.MULTI_HEAD"
+    (src/shift_encoder.py:30-39).  Same accepted inputs (string / flag / int / None / "null"), parsed
+    without eval."""
+    if value is None or value == "" or value == "null":
+        return enum_cls(0)
+    if isinstance(value, enum_cls):
+        return value
+    if isinstance(value, int):
+        return enum_cls(value)
+    out = enum_cls(0)
+    for tok in str(value).split("|"):
+        tok = tok.strip()
+        if not tok:
+            continue
+        m = re.fullmatch(rf"(?:{enum_cls.__name__}\.)?(\w+)", tok)
+        if m and m.group(1) in enum_cls.__members__:
+            out |= enum_cls[m.group(1)]
+        elif re.fullmatch(rf"{enum_cls.__name__}\((\d+)\)|(\d+)", tok):
+            out |= enum_cls(int(re.sub(r"\D", "", tok)))
+        else:
+            raise AttributeError(f"{tok!r} is not a member of {enum_cls.__name__}")
+    return out
+
+
+class RecordPlan:
+    """Where the record hooks put the selected rows of each layer's output.
+
+    rows      int32 [N] device: flat row index (b*S + s) of every selected token, sample-major
+    buffer    [L, N, D] preallocated (bf16 for a bf16 model: the H' buffer of the north star)
+    """
+
+    def __init__(self, rows: torch.Tensor, buffer: torch.Tensor):
+        assert rows.dtype == torch.int32 and buffer.dim() == 3 and buffer.shape[1] == rows.numel()
+        self.rows = rows
+        self.buffer = buffer
+
+
+class BaseHookEncoder(nn.Module):
+    def __init__(self, lmm, attn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy(0),
+                 ffn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy(0)):
+        super().__init__()
+        self.attn_strategy = parse_strategy_flags(attn_strategy)
+        self.ffn_strategy = parse_strategy_flags(ffn_strategy)
+        self.lmm = lmm
+        name = self.lmm.model_name
+        if "idefics-9b" in name:                       # src/shift_encoder.py:42-61
+            cfg = lmm.model.config
+        elif "idefics2-8b" in name or "llava-interleave" in name:
+            cfg = lmm.model.config.text_config
+        else:
+            raise ValueError(f"{name} is not supported")
+        self.lmm_hidden_dim, self.lmm_layers, self.lmm_num_head = (
+            cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads)
+        for prefix in ("attn", "ffn"):
+            strategy = getattr(self, f"{prefix}_strategy")
+            if ShiftStrategy.RECORD_HIDDEN_STATES in strategy:
+                setattr(self, f"{prefix}_hidden_states", [[] for _ in range(self.lmm_layers)])
+            if ShiftStrategy.LEARNABLE_SHIFT_SCALE in strategy and ShiftStrategy.VECTOR_SHIFT not in strategy:
+                raise ValueError(
+                    "ShiftStrategy.LEARNABLE_SHIFT_SCALE should be used with ShiftStrategy.USE_VECTOR_SHIFT")
+        self.record_plan: Optional[Dict[str, RecordPlan]] = None   # per record list; set by ShiftModel
+
+    def register_hooks(self, register_fn_name: str, targets: List[Union[str, HookType]], hooks: Dict[str, Callable]):
+        return {name: getattr(self.lmm, register_fn_name)(target, hook_fn)
+                for target, (name, hook_fn) in zip(targets, hooks.items()) if hook_fn is not None}
+
+    @property
+    def decoder_mlp_name(self) -> str:                 # src/shift_encoder.py:95-102
+        if "idefics-9b" in self.lmm.model_name:
+            return r"model\.layers\.\d+\.mlp$"
+        if "idefics2-8b" in self.lmm.model_name:
+            return r"model\.text_model\.layers\.\d+\.mlp$"
+        if "llava-interleave" in self.lmm.model_name:
+            return r"language_model\.model\.layers\.\d+\.mlp$"
+
+    @property
+    def decoder_self_attn_name(self) -> str:           # src/shift_encoder.py:104-111
+        if "idefics-9b" in self.lmm.model_name:
+            return r"model\.layers\.\d+\.self_attn$"
+        if "idefics2-8b" in self.lmm.model_name:
+            return r"model\.text_model\.layers\.\d+\.self_attn$"
+        if "llava-interleave" in self.lmm.model_name:
+            return r"language_model\.model\.layers\.\d+\.self_attn$"
+
+    def register_record_hooks(self, **kwargs):
+        """src/shift_encoder.py:113-140.  Without a `record_plan` this is the reference behaviour (keep
+        a reference to the module output per layer).  With one, the selected rows are gathered by
+        kernel R into plan.buffer[layer] and `*_hidden_states[layer]` is that [N, D] slice."""
+        def record_hook(m, inputs, outputs, module_name, record_varname, **kw):
+            layer_idx = int(re.findall(r"\d+", module_name)[0])
+            hidden_states = outputs[0] if isinstance(outputs, tuple) else outputs
+            plan = self.record_plan.get(record_varname) if self.record_plan else None
+            if plan is not None and not torch.is_grad_enabled():
+                ops.record_gather(hidden_states, plan.rows, plan.buffer[layer_idx])
+                getattr(self, record_varname)[layer_idx] = plan.buffer[layer_idx]
+            else:
+                getattr(self, record_varname)[layer_idx] = hidden_states
+
+        return self.register_hooks(
+            "register_forward_hook",
+            [self.decoder_self_attn_name, self.decoder_mlp_name],
+            {
+                "attn_record_hook": (partial(record_hook, record_varname="attn_hidden_states")
+                                     if hasattr(self, "attn_hidden_states") else None),
+                "ffn_record_hook": (partial(record_hook, record_varname="ffn_hidden_states")
+                                    if hasattr(self, "ffn_hidden_states") else None),
+            },
+        )
+
+
+class MultiheadLinear(nn.Module):                      # src/shift_encoder.py:547-556
+    def __init__(self, lmm_num_head, lmm_hidden_dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(lmm_num_head, lmm_hidden_dim // lmm_num_head).normal_(0, 0.02))
+        self.bias = nn.Parameter(torch.zeros([lmm_num_head]))
+
+    def forward(self, x):                              # kept for API parity; the kernels read .weight/.bias
+        return torch.einsum("btnd,nd->btn", x, self.weight) + self.bias
+
+
+class AttnApproxHandle:                                # src/shift_encoder.py:572-577
+    def __init__(self, active=False):
+        self.active = active
+
+    def remove(self):
+        self.active = False
+
+
+# --------------------------------------------------------------------------------------------------
+# attention forwards installed by register_shift_hooks
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def _apply_rope(q, k, cos, sin):
+    cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
+    return q * cos + _rotate_half(q) * sin, k * cos + _rotate_half(k) * sin
+
+
+def key_mask_from_4d(attention_mask: Optional[torch.Tensor], T: int, S: int):
+    """HF hands the attention module a 4-D mask [B,1,T,S] (bool: True = attend; float: 0 = attend) or
+    None.  The fused op wants (causal flag, [B,S] key mask).  The last query row sees every valid key."""
+    if attention_mask is None:
+        return (T > 1), None
+    m = attention_mask
+    if m.dim() == 2:                                   # already a [B,S] key mask
+        return (T > 1), m.bool()
+    row = m[:, 0, -1, :S]
+    key_ok = row if row.dtype == torch.bool else (row == 0)
+    return (T > 1), key_ok
+
+
+def _fused_attn_forward(self, hidden_states, position_embeddings=None, attention_mask=None,
+                        past_key_values=None, past_key_value=None, cache_position=None, position_ids=None,
+                        key_value_states=None, module_name=None, shift_encoder=None, old_method=None, **kwargs):
+    """q/k/v projection -> [qk-norm] -> RoPE -> [KV cache] -> fused shifted attention -> o_proj.
+
+    Replaces idefics_attn_forward / idefics2_attn_forward / llava_attn_forward
+    (src/shift_encoder.py:251-381, 386-471, 475-544): everything between RoPE and o_proj is one
+    CUDA op; GQA heads are indexed in-kernel instead of repeat_kv (431-432)."""
+    if key_value_states is not None or getattr(self, "is_cross_attention", False):
+        return old_method(hidden_states, key_value_states=key_value_states, attention_mask=attention_mask, **kwargs)
+    if self.training and float(getattr(self, "attention_dropout", getattr(self, "dropout", 0.0)) or 0.0) > 0.0:
+        raise NotImplementedError("attention dropout > 0 is not supported by the fused shifted attention")
+    if getattr(self, "sliding_window", None) is not None and hidden_states.shape[1] > self.sliding_window:
+        raise NotImplementedError("sliding-window attention is not supported by the fused shifted attention")
+    B, T, _ = hidden_states.shape
+    d = self.head_dim
+    q = self.q_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+    k = self.k_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+    v = self.v_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+    cache = past_key_values if past_key_values is not None else past_key_value
+    if position_embeddings is not None:
+        cos, sin = position_embeddings
+        q, k = _apply_rope(q, k, cos, sin)
+    elif hasattr(self, "rotary_emb"):                  # pre-4.48 module layout (Idefics v1)
+        kv_len = T + (cache.get_seq_length(self.layer_idx) if cache is not None else 0)
+        cos, sin = self.rotary_emb(v, seq_len=max(kv_len, T))
+        pos = position_ids if position_ids is not None else torch.arange(kv_len - T, kv_len, device=q.device)[None]
+        q, k = _apply_rope(q, k, cos[pos], sin[pos])
+    if cache is not None:
+        k, v = cache.update(k, v, self.layer_idx)
+    if getattr(self, "qk_layer_norms", False):         # Idefics v1 option (src/shift_encoder.py:328-330)
+        q, k = self.q_layer_norm(q), self.k_layer_norm(k)
+    S = k.shape[2]
+    layer_idx = int(re.findall(r"\d+", module_name)[0])
+    causal, key_mask = key_mask_from_4d(attention_mask, T, S)
+    if shift_encoder.key_mask_override is not None and shift_encoder.key_mask_override.shape == (B, S):
+        key_mask = shift_encoder.key_mask_override
+    out = shift_encoder.fused_attention(layer_idx, q, k, v, key_mask, causal,
+                                        scale=getattr(self, "scaling", None))
+    out = self.o_proj(out.reshape(B, T, -1))
+    if old_method is not None and "past_key_value" in inspect.signature(old_method).parameters:
+        return out, None, cache                        # 4.45-era contract (idefics / idefics2 forwards)
+    return out, None
+
+
+def idefics_attn_forward(self, hidden_states, key_value_states=None, attention_mask=None, position_ids=None,
+                         past_key_value=None, output_attentions=False, use_cache=False, cache_position=None,
+                         module_name=None, shift_encoder=None, **kwargs):
+    return _fused_attn_forward(self, hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                               past_key_value=past_key_value, cache_position=cache_position,
+                               key_value_states=key_value_states, module_name=module_name,
+                               shift_encoder=shift_encoder, **kwargs)
+
+
+def idefics2_attn_forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                          output_attentions=False, use_cache=False, cache_position=None, module_name=None,
+                          shift_encoder=None, **kwargs):
+    return _fused_attn_forward(self, hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                               past_key_value=past_key_value, cache_position=cache_position,
+                               module_name=module_name, shift_encoder=shift_encoder, **kwargs)
+
+
+def llava_attn_forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_value=None,
+                       cache_position=None, module_name=None, shift_encoder=None, **kwargs):
+    return _fused_attn_forward(self, hidden_states, position_embeddings=position_embeddings,
+                               attention_mask=attention_mask, past_key_value=past_key_value,
+                               cache_position=cache_position, module_name=module_name,
+                               shift_encoder=shift_encoder, **kwargs)
+
+
+class AttnApproximator(BaseHookEncoder):
+    """MimIC attention heads (src/shift_encoder.py:580-732), `mimic.yaml` strategy
+    VECTOR_SHIFT | LEARNABLE_SHIFT_SCALE | MULTI_HEAD on the fused CUDA path."""
+
+    def __init__(self, lmm, attn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy.VECTOR_SHIFT,
+                 ffn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy(0), attn_impl: str = "auto"):
+        super().__init__(lmm, attn_strategy, ffn_strategy)
+        self.attn_shift_handles = [AttnApproxHandle() for _ in range(self.lmm_layers)]
+        self.attn_impl = attn_impl
+        self.key_mask_override: Optional[torch.Tensor] = None
+        self.grad_sinks: Optional[List[ops.GradSink]] = None
+        H, D = self.lmm_num_head, self.lmm_hidden_dim
+        multi = ShiftStrategy.MULTI_HEAD in self.attn_strategy
+        if ShiftStrategy.LEARNABLE_SHIFT_SCALE in self.attn_strategy:
+            self.log_Z1_lin = nn.ModuleList(
+                (MultiheadLinear(H, D) if multi else nn.Linear(D, 1)) for _ in range(self.lmm_layers))
+        if ShiftStrategy.VECTOR_SHIFT in self.attn_strategy:
+            self.attn_shift = nn.Parameter(
+                torch.randn([self.lmm_layers] + ([H, D // H] if multi else [D])) * 0.001)
+        if ShiftStrategy.VECTOR_SHIFT in self.ffn_strategy:
+            self.ffn_shift = nn.Parameter(torch.randn([self.lmm_layers, D]) * 0.001)
+
+    # ---- hooks -------------------------------------------------------------------------------
+    def register_shift_hooks(self, **kwargs):          # src/shift_encoder.py:627-680
+        if ShiftStrategy.VECTOR_SHIFT in self.attn_strategy:
+            if not hasattr(self, "attn_forward_replaced"):
+                name = self.lmm.model_name
+                if name == "idefics-9b":
+                    new_attn_forward = idefics_attn_forward
+                elif "idefics2-8b" in name:
+                    new_attn_forward = idefics2_attn_forward
+                elif "llava-interleave" in name:
+                    new_attn_forward = llava_attn_forward
+                else:
+                    raise ValueError(f"{name} is not supported")
+                self.lmm.replace_module_method(self.decoder_self_attn_name, "forward",
+                                               partial(new_attn_forward, shift_encoder=self), strict=False)
+                setattr(self, "attn_forward_replaced", True)
+            for handle in self.attn_shift_handles:
+                handle.active = True
+        registered_hooks = {"attn_hook": self.attn_shift_handles}
+        if ShiftStrategy.VECTOR_SHIFT in self.ffn_strategy:
+            def hook(m, inputs, outputs, module_name, **kw):
+                layer_idx = int(re.findall(r"\d+", module_name)[0])
+                hidden_states, *rest = outputs if isinstance(outputs, tuple) else (outputs,)
+                shifted = hidden_states + self.ffn_shift[layer_idx][None, None, :]
+                hidden_states = (shifted / shifted.norm(dim=-1, keepdim=True)
+                                 * hidden_states.norm(dim=-1, keepdim=True))
+                return (hidden_states, *rest) if isinstance(outputs, tuple) else hidden_states
+            registered_hooks.update(
+                self.register_hooks("register_forward_hook", [self.decoder_mlp_name], {"ffn_hook": hook}))
+        return registered_hooks
+
+    # ---- the fused op ------------------------------------------------------------------------
+    def _fused_ok(self) -> bool:
+        need = ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD
+        return (self.attn_strategy & need) == need
+
+    def fused_attention(self, layer_idx, q, k, v, key_mask, causal, scale=None):
+        """[B,H,T,d] x [B,Hkv,S,d] -> [B,T,H,d]; plain masked attention when the handle is inactive
+        (src/shift_encoder.py:685, 732)."""
+        active = self.attn_shift_handles[layer_idx].active
+        if active and not self._fused_ok():
+            raise NotImplementedError(
+                "the fused CUDA path implements the mimic.yaml strategy "
+                "(VECTOR_SHIFT | LEARNABLE_SHIFT_SCALE | MULTI_HEAD); got " + repr(self.attn_strategy))
+        if not active:
+            return ops.shifted_attention(q, k, v, None, None, None, key_mask, causal=causal, active=False,
+                                         scale=scale, impl=self.attn_impl)
+        lin = self.log_Z1_lin[layer_idx]
+        sink = self.grad_sinks[layer_idx] if self.grad_sinks is not None else None
+        return ops.shifted_attention(q, k, v, self.attn_shift[layer_idx], lin.weight, lin.bias, key_mask,
+                                     causal=causal, active=True, scale=scale, impl=self.attn_impl, grad_sink=sink)
+
+    def do_shift(self, layer_idx, query_states, key_states, attn_output):
+        """API-parity entry (src/shift_encoder.py:682-732): attn_output [B,T,H,d] + mu(q,K) * shift.
+        The mu term comes from the same fused kernel run with zero values, so that
+        SA == 0 and the kernel returns exactly mu * shift."""
+        if not self.attn_shift_handles[layer_idx].active:
+            return attn_output
+        if not self._fused_ok():
+            raise NotImplementedError("do_shift: only the mimic.yaml strategy is on the CUDA path")
+        lin = self.log_Z1_lin[layer_idx]
+        zeros_v = torch.zeros_like(key_states)
+        term = ops.shifted_attention(query_states, key_states, zeros_v, self.attn_shift[layer_idx], lin.weight,
+                                     lin.bias, None, causal=False, active=True,
+                                     scale=1.0 / (self.lmm_hidden_dim // self.lmm_num_head) ** 0.5,
+                                     impl=self.attn_impl)
+        return attn_output + term.to(attn_output.dtype)

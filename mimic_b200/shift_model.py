@@ -1,0 +1,253 @@
+"""Drop-in mirror of the reference's training module (src/shift_model.py) for the hot path:
+`Strategy`, `ShiftModel.forward(...) -> loss_dict` with keys "loss", "ce_loss", "ffn_mse_loss", and
+the reference's helper methods (`generate_label_mask`, `get_hidden_states`,
+`calculate_layer_wise_loss`, `remove_hooks`) — with the record / alignment-loss / LM-loss
+arithmetic on the CUDA kernels of libmimic_b200.so.
+
+The Lightning shell (optimizer wiring, logging, checkpoint callbacks) is replaced by
+`mimic_b200.trainer`; this class is a plain nn.Module.
+"""
+from __future__ import annotations
+
+import enum
+from contextlib import nullcontext
+from functools import reduce
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .shift_encoder import RecordPlan
+
+
+class Strategy(enum.IntFlag):            # values are API: src/shift_model.py:21-25
+    LAYER_WISE_MSE = 2
+    LAYER_WISE_COS_SIM = 64
+    LOGITS_KL_DIV = 4
+    LM_LOSS = 8
+
+    def has_layer_wise(self):
+        try:
+            self.layer_wise_strategy()
+            return True
+        except ValueError:
+            return False
+
+    def validate(self):
+        layer_wise = [Strategy.LAYER_WISE_MSE, Strategy.LAYER_WISE_COS_SIM]
+        if bin(self & reduce(lambda x, y: x | y, layer_wise)).count("1") > 1:
+            raise ValueError(f"{[e.name for e in layer_wise]} are mutually exclusive.")
+
+    def layer_wise_strategy(self):
+        if Strategy.LAYER_WISE_MSE in self:
+            return "mse_loss"
+        if Strategy.LAYER_WISE_COS_SIM in self:
+            return "cos_sim"
+        raise ValueError("None of layer wise loss strategy is enabled")
+
+
+def _selected_rows(mask: torch.Tensor, capacity: int):
+    """Flat indices of the True entries of `mask` [B,S], ascending, padded with -1 up to `capacity`,
+    and their count — without a host sync (stable sort instead of nonzero)."""
+    flat = mask.reshape(-1)
+    order = torch.sort((~flat).to(torch.uint8), stable=True).indices[:capacity]
+    count = flat.sum()
+    valid = torch.arange(order.numel(), device=mask.device) < count
+    rows = torch.where(valid, order, torch.full_like(order, -1)).to(torch.int32)
+    return rows, count
+
+
+class ShiftModel(nn.Module):
+    def __init__(self, cfg, shift_encoder, strategy: Strategy, save_checkpoint_when=None) -> None:
+        super().__init__()
+        self.lmm = shift_encoder.lmm
+        self.cfg = cfg
+        self.shift_encoder = shift_encoder
+        strategy.validate()
+        self.strategy = strategy
+        self.save_checkpoint_when = save_checkpoint_when
+        self._hp_buffers: Dict[str, torch.Tensor] = {}
+
+    # ---- tokenizer facts -----------------------------------------------------------------------
+    @property
+    def _tok(self):
+        return self.lmm.processor.tokenizer
+
+    @property
+    def device(self):
+        return next(self.lmm.model.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.lmm.model.parameters()).dtype
+
+    # ---- src/shift_model.py:75-110, vectorised on device (no per-sample .item()) ----------------
+    def generate_label_mask(self, inputs, num_separator, keep_bos=False):
+        input_ids = inputs["input_ids"]
+        pad_mask = input_ids == self._tok.pad_token_id
+        non_pad = ~pad_mask
+        left = self._tok.padding_side == "left"
+        if left:
+            bos_position = non_pad.long().argmax(dim=1)
+            sep = pad_mask & (torch.arange(input_ids.shape[1], device=input_ids.device)[None] > bos_position[:, None])
+        else:
+            sep = pad_mask
+        n_sep_before = sep.long().cumsum(dim=1) - sep.long()       # separators strictly before position
+        label_mask = (n_sep_before >= num_separator) & non_pad     # strictly after the n-th separator
+        if getattr(self, "check_separators", True):
+            if bool((sep.sum(dim=1) < num_separator).any()):
+                bad = int((sep.sum(dim=1) < num_separator).nonzero()[0])
+                raise ValueError(f"Sequence {bad} has fewer pad tokens ({int(sep[bad].sum())}) "
+                                 f"than num_separator ({num_separator})")
+        if keep_bos:
+            if not left:
+                raise NameError("bos_position is only defined for left padding (reference behaviour)")
+            label_mask[torch.arange(input_ids.shape[0], device=input_ids.device), bos_position] = True
+        return label_mask
+
+    def remove_hooks(self, hooks):                       # src/shift_model.py:112-119
+        for name, handles in hooks.items():
+            if isinstance(handles, list):
+                for handle in handles:
+                    handle.remove()
+            else:
+                handles.remove()
+
+    # ---- reference-shaped helpers (lists of per-sample tensors), CUDA kernels underneath ---------
+    def get_hidden_states(self, query_label_mask):       # src/shift_model.py:121-143
+        out = {}
+        counts = query_label_mask.sum(dim=1).tolist()
+        rows = query_label_mask.reshape(-1).nonzero().flatten().to(torch.int32)
+        for name, attr in vars(self.shift_encoder).items():
+            if "hidden_states" not in name:
+                continue
+            L, D = len(attr), attr[0].shape[-1]
+            buf = torch.empty(L, rows.numel(), D, dtype=attr[0].dtype, device=attr[0].device)
+            grads = any(t.requires_grad for t in attr)
+            if grads:                                    # keep autograd: differentiable gather
+                for l, t in enumerate(attr):
+                    buf[l] = t.reshape(-1, D).index_select(0, rows.long())
+            else:
+                for l, t in enumerate(attr):
+                    ops.record_gather(t, rows, buf[l])
+            out[name] = list(buf.split(counts, dim=1))
+        if not out:
+            raise RuntimeError("Layer wise loss requires to record hidden states, but no any "
+                               "*_hidden_states in shift encoder.")
+        return out
+
+    def calculate_layer_wise_loss(self, shift_hidden_states, prefix_hidden_states):   # 145-179
+        if Strategy.LAYER_WISE_MSE not in self.strategy:
+            raise NotImplementedError("only Strategy.LAYER_WISE_MSE is on the CUDA path")
+        layer_loss = {}
+        for (name, shift_list), (_, prefix_list) in zip(shift_hidden_states.items(), prefix_hidden_states.items()):
+            per_sample = []
+            for hs, hp in zip(shift_list, prefix_list):
+                L, n, D = hs.shape
+                hs_c = hs.contiguous()
+                idx = torch.arange(n, dtype=torch.int32, device=hs.device)
+                w = torch.full((n,), 1.0 / (L * n * D), dtype=torch.float32, device=hs.device)
+                per_sample.append(ops.align_mse([hs_c[l] for l in range(L)], hp.contiguous(), idx, w))
+            layer_loss[name.replace("hidden_states", self.strategy.layer_wise_strategy())] = \
+                torch.mean(torch.stack(per_sample))
+        return layer_loss
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def forward(self, prefix_texts, query_texts, answers, images):
+        """Reference signature (src/shift_model.py:193): strings + images -> loss_dict.  Builds the
+        two prompts exactly like lines 204-222 and hands token tensors to `forward_inputs`."""
+        tok = self._tok
+        pad, eos = tok.pad_token, tok.eos_token
+        query_answer = [q + pad + a + eos for q, a in zip(query_texts, answers)]
+        query_images = [img[-self.cfg.data.num_image_in_query:] for img in images]
+        query_inputs = self.lmm.process_input(query_images, query_answer).to(device=self.device, dtype=self.dtype)
+        inputs = None
+        if self.strategy != Strategy.LM_LOSS:
+            full_text = [ice + pad + q + pad + a + eos for ice, q, a in zip(prefix_texts, query_texts, answers)]
+            inputs = self.lmm.process_input(images, full_text).to(device=self.device, dtype=self.dtype)
+        return self.forward_inputs(inputs, query_inputs)
+
+    def _hp_buffer(self, name, L, N, D, dtype, device):
+        buf = self._hp_buffers.get(name)
+        if buf is None or buf.shape != (L, N, D) or buf.dtype != dtype or buf.device != device:
+            buf = torch.empty(L, N, D, dtype=dtype, device=device)
+            self._hp_buffers[name] = buf
+        return buf
+
+    def forward_inputs(self, inputs: Optional[dict], query_inputs: dict, fold_scale: float = 1.0):
+        """Token-level MimIC step (src/shift_model.py:200-285).  `inputs` = full-context batch
+        ([bos] ICE [PAD] query [PAD] answer [eos]), `query_inputs` = query-only batch; both dicts of
+        model kwargs containing "input_ids" (attention masks are rebuilt from the pad id like lines
+        212/222).  `fold_scale` multiplies every loss gradient (1/accumulate_grad_batches)."""
+        enc, tok = self.shift_encoder, self._tok
+        if self.strategy & (Strategy.LOGITS_KL_DIV | Strategy.LAYER_WISE_COS_SIM):
+            raise NotImplementedError("LOGITS_KL_DIV / LAYER_WISE_COS_SIM are not on the CUDA path yet")
+        loss_dict = {"loss": 0.0}
+        hooks = enc.register_record_hooks()
+        q_ids = query_inputs["input_ids"]
+        B, T = q_ids.shape
+        query_inputs = dict(query_inputs)
+        query_inputs["attention_mask"] = q_ids != tok.pad_token_id
+        layer_wise = self.strategy.has_layer_wise()
+        record_names = [n for n in vars(enc) if "hidden_states" in n]
+        N_cap = B * T
+
+        if self.strategy != Strategy.LM_LOSS:
+            inputs = dict(inputs)
+            inputs["attention_mask"] = inputs["input_ids"] != tok.pad_token_id
+            if layer_wise:
+                if not record_names:
+                    raise RuntimeError("Layer wise loss requires to record hidden states, but no any "
+                                       "*_hidden_states in shift encoder.")
+                rows_ctx, n_ctx = _selected_rows(self.generate_label_mask(inputs, 1), N_cap)
+                # one [L, N_cap, D] H' buffer; with two record points the hook order is attn then mlp per layer
+                D, L = enc.lmm_hidden_dim, enc.lmm_layers
+                plans = {n: RecordPlan(rows_ctx, self._hp_buffer(n, L, N_cap, D, self.dtype, q_ids.device))
+                         for n in record_names}
+                enc.record_plan = plans
+            # step 1: full-context forward, no grad, adapters off (line 225-226); hooks gather H' rows
+            enc.key_mask_override = inputs["attention_mask"]
+            with torch.no_grad(), getattr(self.lmm.model, "disable_adapter", nullcontext)():
+                self.lmm.model(**inputs)
+            enc.record_plan = None
+
+        # step 2: shifted query forward (lines 237-243)
+        hooks.update(enc.register_shift_hooks())
+        enc.key_mask_override = query_inputs["attention_mask"]
+        out = self.lmm.model(**query_inputs)
+        enc.key_mask_override = None
+        logits = out["logits"] if not isinstance(out, torch.Tensor) else out
+
+        if Strategy.LM_LOSS in self.strategy:
+            w = 1.0 if self.strategy == Strategy.LM_LOSS else float(self.cfg.ce_loss_weight)
+            labels = torch.full_like(q_ids, -100)
+            labels[:, :-1] = torch.where(query_inputs["attention_mask"][:, 1:], q_ids[:, 1:],
+                                         torch.full_like(q_ids[:, 1:], -100))
+            ce = ops.ce_loss(logits, labels, grad_scale=w * fold_scale, assume_folded=True)
+            loss_dict["ce_loss"] = ce.detach()
+            loss_dict["loss"] = loss_dict["loss"] + w * ce
+
+        if layer_wise:
+            mq = query_inputs["attention_mask"] & (q_ids != tok.bos_token_id)     # lines 253-257
+            flat = mq.reshape(-1)
+            rank = flat.long().cumsum(0) - 1
+            row_to_compact = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32)
+            nq = mq.sum(dim=1).clamp_min(1).float()                               # [B]
+            D, L = enc.lmm_hidden_dim, enc.lmm_layers
+            w_row = (1.0 / (B * L * D)) / nq                                      # weight of a row of sample b
+            rows_q, _ = _selected_rows(mq, N_cap)
+            row_w = w_row[(rows_q.clamp_min(0) // T).long()]
+            aw = float(self.cfg.align_loss_weight)
+            layer_loss = {}
+            for n in record_names:
+                hs = list(getattr(enc, n))
+                mse = ops.align_mse(hs, self._hp_buffers[n], row_to_compact, row_w,
+                                    grad_scale=aw * fold_scale, assume_folded=True)
+                layer_loss[n.replace("hidden_states", self.strategy.layer_wise_strategy())] = mse
+            for k_, v_ in layer_loss.items():
+                loss_dict[k_] = v_.detach()
+            loss_dict["loss"] = loss_dict["loss"] + aw * sum(layer_loss.values())
+
+        self.remove_hooks(hooks)
+        return loss_dict

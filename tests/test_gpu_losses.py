@@ -1,0 +1,157 @@
+"""Parity of the HBM-bound kernels (record gather, fused MSE, fused CE, AdamW) with the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import losses as OL
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("dtype,dst", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                       (torch.float32, torch.bfloat16)])
+def test_record_gather(dtype, dst):
+    from mimic_b200 import ops
+    torch.manual_seed(0)
+    src = torch.randn(3, 50, 256, device="cuda").to(dtype)
+    rows = torch.tensor([0, 7, 149, 33, -1, 50], dtype=torch.int32, device="cuda")
+    out = torch.full((6, 256), 7.0, dtype=dst, device="cuda")
+    ops.record_gather(src, rows, out)
+    want = src.reshape(-1, 256)[rows.clamp_min(0).long()].to(dst)
+    want[4] = 0
+    assert torch.equal(out, want)
+
+
+def _mse_case(dtype, L, B, T, D, counts, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    hs = [torch.randn(B, T, D, generator=g).to(dtype) for _ in range(L)]
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    for b, c in enumerate(counts):
+        mask[b, T - c:] = True
+    N = int(mask.sum())
+    hp = torch.randn(L, N, D, generator=g).to(dtype)
+    return hs, mask, hp
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(3, 2, 8, 64, (5, 6)), (4, 2, 40, 1024, (33, 17)), (2, 1, 16, 4096, (16,))])
+def test_align_mse_matches_oracle(dtype, shape):
+    from mimic_b200 import ops
+    L, B, T, D, counts = shape
+    hs, mask, hp = _mse_case(dtype, L, B, T, D, counts)
+    # oracle on the same (rounded) values, fp32
+    hs32 = [h.float().requires_grad_(True) for h in hs]
+    want = OL.layer_wise_mse(OL.get_hidden_states(hs32, mask),
+                             [t for t in hp.float().split([int(c) for c in counts], dim=1)])
+    wg = torch.autograd.grad(want, hs32)
+    flat = mask.reshape(-1)
+    rank = flat.long().cumsum(0) - 1
+    r2c = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32).cuda()
+    w_rows = torch.cat([torch.full((c,), 1.0 / (B * L * c * D)) for c in counts]).cuda()
+    hs_c = [h.cuda().requires_grad_(True) for h in hs]
+    loss = ops.align_mse(hs_c, hp.cuda(), r2c, w_rows)
+    grads = torch.autograd.grad(loss, hs_c)
+    assert abs(float(loss) - float(want)) <= 2e-6 * abs(float(want))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b in zip(grads, wg):
+        assert rel(a, b) < tol
+        assert float(a[~mask.cuda()].abs().max()) == 0.0          # grad lands only on selected rows
+    # folded upstream scale
+    hs_c2 = [h.cuda().requires_grad_(True) for h in hs]
+    loss2 = ops.align_mse(hs_c2, hp.cuda(), r2c, w_rows, grad_scale=0.25, assume_folded=True)
+    g2 = torch.autograd.grad(loss2 * 0.25, hs_c2)
+    for a, b in zip(g2, wg):
+        assert rel(a, 0.25 * b) < tol
+
+
+def test_align_mse_reference_golden():
+    """The exact ragged case the reference produced (tests/golden/loss_pieces.npz)."""
+    from mimic_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "loss_pieces.npz"))
+    qry = torch.from_numpy(z["qry"]).cuda()                    # [L,B,T,D]
+    mask_q = torch.from_numpy(z["mask_q"]).bool()
+    hp = torch.cat([torch.from_numpy(z["hp0"]), torch.from_numpy(z["hp1"])], dim=1).cuda()
+    L, B, T, D = qry.shape
+    counts = mask_q.sum(1).tolist()
+    flat = mask_q.reshape(-1)
+    rank = flat.long().cumsum(0) - 1
+    r2c = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32).cuda()
+    w_rows = torch.cat([torch.full((c,), 1.0 / (B * L * c * D)) for c in counts]).cuda()
+    hs = [qry[l].clone().requires_grad_(True) for l in range(L)]
+    loss = ops.align_mse(hs, hp, r2c, w_rows)
+    grads = torch.stack(torch.autograd.grad(loss, hs))
+    assert abs(float(loss) - float(z["ffn_mse_loss"])) < 2e-6 * float(z["ffn_mse_loss"])
+    assert rel(grads, torch.from_numpy(z["dqry"])) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (5, 151655), (300, 513)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_ce_matches_oracle(dtype, R, V, inplace):
+    from mimic_b200 import ops
+    g = torch.Generator().manual_seed(R + V)
+    logits = (torch.randn(R, V, generator=g) * 3).to(dtype)
+    labels = torch.randint(0, V, (R,), generator=g)
+    labels[::3] = -100
+    l32 = logits.float().requires_grad_(True)
+    want = F.cross_entropy(l32, labels, ignore_index=-100)
+    wg, = torch.autograd.grad(want, l32)
+    lc = logits.cuda().requires_grad_(True)
+    x = lc * 1.0 if inplace else lc          # in-place needs a non-leaf
+    loss = ops.ce_loss(x, labels.cuda(), inplace=inplace)
+    got, = torch.autograd.grad(loss, lc)
+    assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want)) + 1e-6
+    assert rel(got, wg) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert float(got[labels.cuda() < 0].abs().max()) == 0.0
+
+
+def test_ce_all_ignored_and_lm_rule():
+    from mimic_b200 import ops
+    logits = torch.randn(4, 33, device="cuda", requires_grad=True)
+    loss = ops.ce_loss(logits, torch.full((4,), -100, device="cuda"))
+    assert float(loss) == 0.0
+    # the LM rule of oracle.losses.lm_ce_loss, built the way ShiftModel.forward_inputs builds labels
+    torch.manual_seed(3)
+    B, T, V = 2, 9, 17
+    lg = torch.randn(B, T, V)
+    ids = torch.randint(1, V, (B, T))
+    am = torch.ones(B, T, dtype=torch.bool)
+    am[0, :3] = False
+    am[1, 5] = False
+    want = OL.lm_ce_loss(lg, ids, am)
+    labels = torch.full_like(ids, -100)
+    labels[:, :-1] = torch.where(am[:, 1:], ids[:, 1:], torch.full_like(ids[:, 1:], -100))
+    got = ops.ce_loss(lg.cuda(), labels.cuda())
+    assert abs(float(got) - float(want)) < 1e-5
+
+
+def test_adamw_step_matches_torch():
+    from mimic_b200 import ops
+    torch.manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n)
+    wd = torch.where(torch.arange(n) % 5 == 0, torch.zeros(n), torch.full((n,), 1e-3))
+    pa = torch.nn.Parameter(p0[wd == 0].clone())
+    pb = torch.nn.Parameter(p0[wd != 0].clone())
+    opt = torch.optim.AdamW([{"params": [pa], "weight_decay": 0.0}, {"params": [pb], "weight_decay": 1e-3}], lr=5e-3)
+    p = p0.clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr = torch.tensor([5e-3], device="cuda")
+    for step in range(1, 4):
+        g = torch.randn(n) * 3
+        pa.grad, pb.grad = g[wd == 0].clone(), g[wd != 0].clone()
+        torch.nn.utils.clip_grad_norm_([pa, pb], 1.0)
+        opt.step()
+        ops.adamw_step(p, g.cuda(), m, v, wd.cuda(), lr, step, max_norm=1.0)
+        want = torch.empty(n)
+        want[wd == 0], want[wd != 0] = pa.detach(), pb.detach()
+        assert rel(p, want) < 1e-6

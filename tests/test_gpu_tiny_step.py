@@ -1,0 +1,50 @@
+"""BASELINE config 1: the full MimIC step on the tiny random-init decoder, CUDA path vs what the
+REFERENCE produced through its own hooks (tests/golden/tiny_step.npz, made by oracle/gen_golden.py)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_tiny_step_matches_reference():
+    from oracle.gen_golden import _Tok, tiny_qwen2
+    from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy, ops
+    z = np.load(os.path.join(GOLDEN, "tiny_step.npz"))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = tiny_qwen2()
+    wsum = sum(float(p.double().abs().sum()) for p in model.parameters())
+    assert abs(wsum - float(z["weights_checksum"])) < 1e-6 * wsum, "random-init backbone differs from the fixture's"
+    lmm = HookedModel(model.cuda(), "llava-interleave-qwen-7b-hf", processor=types.SimpleNamespace(tokenizer=_Tok()))
+    enc = AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+                           "ShiftStrategy.RECORD_HIDDEN_STATES").cuda()
+    sd = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}
+    missing = enc.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if not k.startswith("lmm")]
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0,
+                                data=types.SimpleNamespace(num_image_in_query=1))
+    sm = ShiftModel(cfg, enc, Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    full_ids, qa_ids = torch.from_numpy(z["full_ids"]).cuda(), torch.from_numpy(z["qa_ids"]).cuda()
+    n0 = ops.launch_count
+    loss_dict = sm.forward_inputs({"input_ids": full_ids}, {"input_ids": qa_ids})
+    assert set(loss_dict) == {"loss", "ce_loss", "ffn_mse_loss"}
+    assert abs(float(loss_dict["ce_loss"]) - float(z["ce_loss"])) < 2e-5 * float(z["ce_loss"])
+    assert abs(float(loss_dict["ffn_mse_loss"]) - float(z["ffn_mse_loss"])) < 1e-4 * float(z["ffn_mse_loss"])
+    assert abs(float(loss_dict["loss"]) - float(z["loss"])) < 2e-5 * float(z["loss"])
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    grads = torch.autograd.grad(loss_dict["loss"], list(params.values()))
+    assert ops.launch_count - n0 >= 4 * 2 + 4 + 2 + 2 + 4 * 3      # attn fwd x2 passes, gathers, mse, ce, attn bwd
+    for (n, p), g in zip(params.items(), grads):
+        assert rel(g, z["grad." + n]) < 2e-4, n
+    # handles are inactive again, hooks removed (src/shift_model.py:262)
+    assert not any(h.active for h in enc.attn_shift_handles)

@@ -1,0 +1,200 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/mimic_b200.h declares, and
+the host-side mirror of the reference interface (strategy parsing, hook API, label masks, state
+dict keys, error behaviour) matches the reference / oracle.  No GPU compute calls."""
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import losses as OL
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MIMIC = ("ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+         "ShiftStrategy.RECORD_HIDDEN_STATES")
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from mimic_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "mimic_b200.h")).read()
+    declared = set(re.findall(r"MIMIC_API\s+[\w\s\*]+?\b(mimic_\w+)\s*\(", header))
+    assert len(declared) >= 11
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.mimic_abi_version() == 1
+
+
+def test_ops_refuse_cpu_tensors():
+    from mimic_b200 import ops
+    from mimic_b200._lib import MimicError
+    t = torch.zeros(1, 1, 8, 32)
+    with pytest.raises(MimicError):
+        ops.shifted_attention(t, t, t, active=False)
+    with pytest.raises(MimicError):
+        ops.ce_loss(torch.zeros(2, 5), torch.zeros(2, dtype=torch.long))
+
+
+def _tiny_lmm(name="llava-interleave-qwen-7b-hf", layers=2):
+    from mimic_b200 import HookedModel
+
+    class Attn(nn.Module):
+        def forward(self, x, **kw):
+            return x * 2, None
+
+    class Layer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attn, self.mlp = Attn(), nn.Linear(8, 8)
+
+        def forward(self, x):
+            return self.mlp(self.self_attn(x)[0])
+
+    class Inner(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.ModuleList(Layer() for _ in range(layers))
+
+        def forward(self, x):
+            for l in self.layers:
+                x = l(x)
+            return x
+
+    class LM(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = Inner()
+
+    class Top(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.language_model = LM()
+            tc = types.SimpleNamespace(hidden_size=8, num_hidden_layers=layers, num_attention_heads=2)
+            self.config = types.SimpleNamespace(text_config=tc)
+
+        def forward(self, x):
+            return self.language_model.model(x)
+
+    return HookedModel(Top(), name)
+
+
+def test_strategy_parsing_matches_reference_semantics():
+    from mimic_b200.shift_encoder import ShiftStrategy, parse_strategy_flags
+    assert parse_strategy_flags(MIMIC[0]) == ShiftStrategy(1 | 8 | 16)
+    assert parse_strategy_flags("null") == ShiftStrategy(0) and parse_strategy_flags(None) == ShiftStrategy(0)
+    assert parse_strategy_flags(ShiftStrategy.VECTOR_SHIFT) == ShiftStrategy.VECTOR_SHIFT
+    assert parse_strategy_flags("ShiftStrategy(0)") == ShiftStrategy(0)
+    with pytest.raises(AttributeError):           # reference: eval raises AttributeError too (attn_shift_ffn_mse.yaml:5)
+        parse_strategy_flags("ShiftStrategy.LEARNABLE_SCALE")
+    assert [int(x) for x in (ShiftStrategy.VECTOR_SHIFT, ShiftStrategy.RECORD_HIDDEN_STATES,
+                             ShiftStrategy.LEARNABLE_SHIFT_SCALE, ShiftStrategy.MULTI_HEAD)] == [1, 4, 8, 16]
+
+
+def test_encoder_contract_state_dict_and_errors():
+    from mimic_b200 import AttnApproximator, Strategy
+    lmm = _tiny_lmm()
+    enc = AttnApproximator(lmm, *MIMIC)
+    keys = {k for k in enc.state_dict() if not k.startswith("lmm")}
+    assert keys == {"attn_shift", "log_Z1_lin.0.weight", "log_Z1_lin.0.bias", "log_Z1_lin.1.weight", "log_Z1_lin.1.bias"}
+    assert enc.attn_shift.shape == (2, 2, 4) and enc.log_Z1_lin[0].weight.shape == (2, 4)
+    assert isinstance(enc.ffn_hidden_states, list) and len(enc.ffn_hidden_states) == 2 and not hasattr(enc, "attn_hidden_states")
+    with pytest.raises(ValueError):
+        AttnApproximator(_tiny_lmm("gpt2"), *MIMIC)
+    with pytest.raises(ValueError):
+        AttnApproximator(lmm, "ShiftStrategy.LEARNABLE_SHIFT_SCALE", None)
+    assert [int(s) for s in (Strategy.LAYER_WISE_MSE, Strategy.LOGITS_KL_DIV, Strategy.LM_LOSS, Strategy.LAYER_WISE_COS_SIM)] == [2, 4, 8, 64]
+    with pytest.raises(ValueError):
+        (Strategy.LAYER_WISE_MSE | Strategy.LAYER_WISE_COS_SIM).validate()
+
+
+@pytest.mark.needs_reference
+def test_state_dict_keys_equal_reference():
+    from mimic_b200 import AttnApproximator
+    ref = ref_loader.make_ref_encoder(8, 2, 2)
+    mine = AttnApproximator(_tiny_lmm(), *MIMIC)
+    rk = {k: tuple(v.shape) for k, v in ref.state_dict().items() if not k.startswith("lmm")}
+    mk = {k: tuple(v.shape) for k, v in mine.state_dict().items() if not k.startswith("lmm")}
+    assert rk == mk
+    mine.load_state_dict({k: v for k, v in ref.state_dict().items() if not k.startswith("lmm")}, strict=False)
+
+
+def test_hook_api_record_and_replace():
+    from mimic_b200 import AttnApproximator
+    lmm = _tiny_lmm()
+    enc = AttnApproximator(lmm, *MIMIC)
+    hooks = enc.register_record_hooks()
+    assert list(hooks) == ["ffn_record_hook"] and len(hooks["ffn_record_hook"]) == 2
+    x = torch.randn(1, 3, 8)
+    lmm.model(x)
+    assert all(isinstance(t, torch.Tensor) and t.shape == (1, 3, 8) for t in enc.ffn_hidden_states)
+    for h in hooks["ffn_record_hook"]:
+        h.remove()
+    # replace_module_method injects module_name / old_method like the reference (model_base.py:730-739)
+    seen = {}
+
+    def new_forward(self, x, module_name=None, old_method=None, **kw):
+        seen[module_name] = old_method
+        return old_method(x)
+
+    lmm.replace_module_method(enc.decoder_self_attn_name, "forward", new_forward, strict=False)
+    lmm.model(x)
+    assert sorted(seen) == ["language_model.model.layers.0.self_attn", "language_model.model.layers.1.self_attn"]
+    with pytest.raises(ValueError):
+        lmm.replace_module_method(r"no_such_module$", "forward", new_forward)
+    reg = enc.register_shift_hooks()
+    assert list(reg) == ["attn_hook"] and all(h.active for h in reg["attn_hook"])
+    for h in reg["attn_hook"]:
+        h.remove()
+    assert not any(h.active for h in enc.attn_shift_handles)
+
+
+def test_generate_label_mask_matches_oracle_and_golden():
+    from mimic_b200 import AttnApproximator, ShiftModel, Strategy
+    z = np.load(os.path.join(ROOT, "tests", "golden", "loss_pieces.npz"))
+    lmm = _tiny_lmm()
+    lmm.processor = types.SimpleNamespace(tokenizer=types.SimpleNamespace(pad_token_id=0, bos_token_id=1, padding_side="left"))
+    sm = ShiftModel(types.SimpleNamespace(), AttnApproximator(lmm, *MIMIC), Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    ids = torch.from_numpy(z["ids"])
+    for n in (1, 2):
+        assert torch.equal(sm.generate_label_mask({"input_ids": ids}, n), torch.from_numpy(z[f"label_mask_sep{n}"]).bool())
+    assert torch.equal(sm.generate_label_mask({"input_ids": ids}, 1, keep_bos=True),
+                       torch.from_numpy(z["label_mask_sep1_keep_bos"]).bool())
+    with pytest.raises(ValueError):
+        sm.generate_label_mask({"input_ids": ids}, 3)
+    g = torch.Generator().manual_seed(5)
+    for side in ("left", "right"):
+        lmm.processor.tokenizer.padding_side = side
+        for _ in range(20):
+            ids = torch.randint(0, 4, (3, 17), generator=g)
+            ids[:, 8] = 0
+            ids[:, 12] = 0
+            ids[:, 3] = 2
+            want = OL.generate_label_mask(ids, 0, 2, padding_side=side)
+            assert torch.equal(sm.generate_label_mask({"input_ids": ids}, 2), want)
+
+
+def test_selected_rows_without_sync():
+    from mimic_b200.shift_model import _selected_rows
+    m = torch.tensor([[0, 1, 1, 0], [1, 0, 0, 1]], dtype=torch.bool)
+    rows, count = _selected_rows(m, 6)
+    assert rows.tolist() == [1, 2, 4, 7, -1, -1] and int(count) == 4
+
+
+def test_key_mask_from_4d():
+    from mimic_b200.shift_encoder import key_mask_from_4d
+    B, T, S = 2, 3, 5
+    km = torch.tensor([[0, 1, 1, 1, 1], [1, 1, 0, 1, 1]], dtype=torch.bool)
+    causal = torch.tril(torch.ones(T, S, dtype=torch.bool), diagonal=S - T)
+    m4 = (km[:, None, None, :] & causal[None, None])
+    c, k = key_mask_from_4d(m4, T, S)
+    assert c and torch.equal(k, km)
+    add = torch.zeros(B, 1, T, S).masked_fill(~m4, torch.finfo(torch.float32).min)
+    c, k = key_mask_from_4d(add, T, S)
+    assert c and torch.equal(k, km)
+    assert key_mask_from_4d(None, 1, S) == (False, None)
