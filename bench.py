@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py — MimIC train step throughput on B200 (BASELINE.json metric: train tokens/s).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (rank 0 only)
+
+Workload at N=1 (BASELINE.json configs[1]): Idefics2-8B shapes (Mistral text tower L=32, D=4096,
+H=32, KV=8, d=128, inter 14336, V=32003, random-init bf16, frozen), MimIC shifted attention +
+LAYER_WISE_MSE + LM loss train step, synthetic VQAv2-like token batch: B=2 per GPU, 3200-token
+32-shot context pass (no grad, record H') + 128-token shifted query pass (grad), clip, AdamW.
+A "step" is one optimizer step on one such micro-batch.  tokens = B * (S_ctx + T_q) per GPU per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "idefics2-8b": dict(preset="idefics2-8b", B=2, S_ctx=3200, T_q=128),
+    "idefics-9b": dict(preset="idefics-9b", B=2, S_ctx=1024, T_q=32),
+    "llava-interleave-7b": dict(preset="llava-interleave-7b", B=2, S_ctx=8192, T_q=768),
+    "tiny": dict(preset="tiny", B=2, S_ctx=512, T_q=64),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(wl, sample_layers: int, threads: int):
+    """The reference's path on host cores (oracle port), bounded sample; see oracle/cpu_step.py."""
+    import torch
+    from mimic_b200.backbone import PRESETS, synthetic_batch
+    from oracle.cpu_step import cpu_mimic_step, cpu_tokens_per_s
+    torch.set_num_threads(threads)
+    kw = PRESETS[wl["preset"]][1]
+    full, qa = synthetic_batch(wl["B"], wl["S_ctx"], wl["T_q"], kw["vocab_size"])
+    step = cpu_mimic_step(full, qa, D=kw["hidden_size"], inter=kw["intermediate_size"], H=kw["num_attention_heads"],
+                          Hkv=kw["num_key_value_heads"], vocab=kw["vocab_size"], n_layers=sample_layers,
+                          model_layers=kw["num_hidden_layers"])
+    return cpu_tokens_per_s(step), step
+
+
+def run_reference(args, wl):
+    """Reference arm: the reference's own (CPU, PyTorch) implementation of the path, all host threads.
+    Rank 0 alone works; the other ranks exit 0."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        v, last = cpu_baseline(wl, args.cpu_layers, threads)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    sample = (f"{last['n_layers']} of {last['model_layers']} decoder layers at the full token shape "
+              f"(B={wl['B']}, S_ctx={wl['S_ctx']}, T_q={wl['T_q']}), per-layer time x depth + LM head/CE once; "
+              f"oracle port of SDPA+do_shift / masked_select+mse_loss / CE, torch CPU fp32")
+    line = {"impl": "reference", "metric": "MimIC train tokens/s", "value": value, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * last["tokens"] / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, **{k: wl[k] for k in ("B", "S_ctx", "T_q")}},
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mimic", choices=["mimic", "reference"])
+    ap.add_argument("--workload", default="idefics2-8b", choices=list(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=None, help="debug: override the number of decoder layers")
+    ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--cpu-layers", type=int, default=1, help="decoder layers in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import mimic_b200
+    from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy, ops
+    from mimic_b200.backbone import build_synthetic, synthetic_batch, synthetic_processor
+    from mimic_b200.trainer import MimicTrainer
+    import types
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    model, model_name = build_synthetic(wl["preset"], device=dev, num_layers=args.layers)
+    cfgm = model.config
+    lmm = HookedModel(model, model_name, processor=synthetic_processor())
+    enc = AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+                           "ShiftStrategy.RECORD_HIDDEN_STATES", attn_impl=args.attn_impl).to(dev)
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0, data=types.SimpleNamespace(num_image_in_query=1))
+    sm = ShiftModel(cfg, enc, Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    trainer = MimicTrainer(sm, lr=5e-3, weight_decay=1e-3, warmup_step=0.1, total_steps=1000, grad_clip_val=1.0,
+                           accumulate_grad_batches=1)
+    B, S, T = wl["B"], wl["S_ctx"], wl["T_q"]
+    full_h, qa_h = synthetic_batch(B, S, T, cfgm.vocab_size, seed=3407 + rank)
+    full_pin, qa_pin = full_h.pin_memory(), qa_h.pin_memory()
+    full_d, qa_d = full_h.to(dev), qa_h.to(dev)
+
+    def step_resident():
+        trainer.micro_step({"input_ids": full_d}, {"input_ids": qa_d})
+
+    def step_e2e():
+        f = full_pin.to(dev, non_blocking=True)
+        q = qa_pin.to(dev, non_blocking=True)
+        trainer.micro_step({"input_ids": f}, {"input_ids": q})
+        return trainer.logged_scalars()          # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # started before warm-up: process start-up stays out of the timed region
+    for _ in range(args.warmup):
+        step_resident()
+    if rank == 0:
+        sampler.rows.clear()                # keep only samples taken from here on (timed region)
+    ops.timer.enabled = True
+    ops.timer.reset()
+    n0 = ops.launch_count
+    ms = timed(step_resident, args.steps)
+    launches = ops.launch_count - n0
+    ops.timer.enabled = False
+    ksum = ops.timer.summary()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    scal = trainer.logged_scalars()
+
+    tokens_per_step = B * (S + T) * world
+    value = tokens_per_step / (ms / args.steps / 1e3)
+    e2e = tokens_per_step / (ms_e2e / args.steps / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    H, d, L = cfgm.num_attention_heads, cfgm.head_dim, cfgm.num_hidden_layers
+    # dominant own kernel: the context-pass attention forward (inactive handle, causal), 2*B*H*S^2*d FLOPs
+    key_ctx = f"attn_fwd_inactive_T{S}_S{S}"
+    n_l, mean_ms, tot_ms = ksum.get(key_ctx, (0, float("nan"), 0.0))
+    flops = 2.0 * B * H * S * S * d
+    achieved = flops / (mean_ms * 1e-3) / 1e12 if n_l else None
+    roofline = {"kernel": f"shifted_attn_fwd[{mimic_b200._lib.last_attn_impl()}] context pass (active=0, causal, S={S})",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+                "peak_source": peaks["src"] + " sustained bf16 (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": flops, "launches": n_l, "mean_ms": mean_ms,
+                "share_of_step": tot_ms / ms if n_l else None}
+    own = {k: {"launches": v[0], "mean_ms": round(v[1], 4), "total_ms": round(v[2], 3)} for k, v in sorted(ksum.items())}
+    # HBM-bound kernels, algorithmic bytes: MSE 3*N*2B, CE 2*R*V*2B
+    extra = {}
+    if "mse_fwd_bwd" in ksum:
+        n_el = L * B * T * cfgm.hidden_size
+        extra["mse_fwd_bwd"] = {"bound": "hbm", "achieved_gbs": 3 * n_el * 2 / (ksum["mse_fwd_bwd"][1] * 1e-3) / 1e9,
+                                "peak": peaks["hbm"], "note": "includes the 1-block partial-sum launch"}
+    if "ce_fwd_bwd" in ksum:
+        extra["ce_fwd_bwd"] = {"bound": "hbm", "achieved_gbs": 2 * B * T * cfgm.vocab_size * 2 / (ksum["ce_fwd_bwd"][1] * 1e-3) / 1e9,
+                               "peak": peaks["hbm"]}
+    line = {
+        "metric": "MimIC train tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload} shapes, MimIC shifted attention + LAYER_WISE_MSE + LM loss train step, "
+                               f"synthetic VQAv2-like batch", "B_per_gpu": B, "S_ctx": S, "T_q": T,
+                   "layers": L, "attn_impl": mimic_b200._lib.last_attn_impl(), "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2: every step streams the 14.5 GB frozen backbone"},
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": (full_pin.numel() + qa_pin.numel()) * 8,
+                "d2h_bytes_per_step": 4 * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "own_kernels": own, "hbm_kernels": extra,
+        "tokens_per_s_per_gpu": value / world, "losses": scal,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, stp = cpu_baseline(wl, args.cpu_layers, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                "sample": f"{stp['n_layers']} of {stp['model_layers']} decoder layers at the full token "
+                                          f"shape, per-layer time x depth + LM head/CE once (oracle/cpu_step.py)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,262 @@
+"""Synthetic frozen backbones with the module layout of the three reference targets, for
+measurement and tests (there is no network for checkpoints): random-init weights of the named
+architecture, module names matched by the reference's regexes (src/shift_encoder.py:95-111).
+
+  idefics2-8b  : model.text_model.layers.N.{self_attn,mlp}      Mistral-7B text tower (GQA 32:8)
+  idefics-9b   : model.layers.N.{self_attn,mlp}                 LLaMA-7B  (MHA)
+  llava-interleave-qwen-7b : language_model.model.layers.N.*    Qwen2-7B  (MHA here, q/k/v bias)
+
+The backbone GEMMs are stock PyTorch (cuBLAS): out of scope for hand-written kernels (SURVEY.md
+§8d).  The stock `Attention.forward` below is plain SDPA — it is what runs until
+`AttnApproximator.register_shift_hooks()` replaces it, exactly like an HF attention module.
+"""
+from __future__ import annotations
+
+import types
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+@dataclass
+class DecoderConfig:
+    hidden_size: int = 4096
+    intermediate_size: int = 14336
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    num_key_value_heads: int = 8
+    vocab_size: int = 32003
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    attention_bias: bool = False
+    attention_dropout: float = 0.0
+    head_dim: Optional[int] = None
+    initializer_range: float = 0.02
+    _attn_implementation: str = "sdpa"
+    use_sliding_window: bool = False
+    sliding_window: Optional[int] = None
+
+    def __post_init__(self):
+        if self.head_dim is None:
+            self.head_dim = self.hidden_size // self.num_attention_heads
+        self.text_config = self
+
+
+PRESETS = {
+    # name: (model_name for the encoder's substring match, config kwargs)
+    "idefics2-8b": ("idefics2-8b-base", dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                                             num_attention_heads=32, num_key_value_heads=8, vocab_size=32003)),
+    "idefics-9b": ("idefics-9b", dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                                      num_attention_heads=32, num_key_value_heads=32, vocab_size=32002,
+                                      rms_norm_eps=1e-6)),
+    "llava-interleave-7b": ("llava-interleave-qwen-7b-hf", dict(hidden_size=4096, intermediate_size=11008,
+                                                                num_hidden_layers=32, num_attention_heads=32,
+                                                                num_key_value_heads=32, vocab_size=152000,
+                                                                rms_norm_eps=1e-6, attention_bias=True,
+                                                                rope_theta=1e6)),
+    "tiny": ("idefics2-8b-tiny", dict(hidden_size=256, intermediate_size=512, num_hidden_layers=4,
+                                      num_attention_heads=8, num_key_value_heads=8, vocab_size=512)),
+}
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim, eps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x):
+        return F.rms_norm(x, (x.shape[-1],), self.weight, self.eps)
+
+
+def rope_cos_sin(position_ids: torch.Tensor, head_dim: int, theta: float, dtype):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=position_ids.device, dtype=torch.float32) / head_dim))
+    ang = position_ids[..., None].float() * inv                       # [B,T,d/2]
+    emb = torch.cat((ang, ang), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+class Attention(nn.Module):
+    def __init__(self, cfg: DecoderConfig, layer_idx: int):
+        super().__init__()
+        self.config, self.layer_idx = cfg, layer_idx
+        self.head_dim = cfg.head_dim
+        self.num_key_value_groups = cfg.num_attention_heads // cfg.num_key_value_heads
+        self.scaling = self.head_dim ** -0.5
+        self.attention_dropout = cfg.attention_dropout
+        self.is_causal = True
+        self.sliding_window = None
+        D, H, KV, d = cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        self.q_proj = nn.Linear(D, H * d, bias=cfg.attention_bias)
+        self.k_proj = nn.Linear(D, KV * d, bias=cfg.attention_bias)
+        self.v_proj = nn.Linear(D, KV * d, bias=cfg.attention_bias)
+        self.o_proj = nn.Linear(H * d, D, bias=False)
+
+    def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        """Stock path (what the reference's un-replaced HF module does): SDPA with a causal+key mask."""
+        B, T, _ = hidden_states.shape
+        d = self.head_dim
+        q = self.q_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+        k = self.k_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+        v = self.v_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+        cos, sin = position_embeddings
+        cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
+        q, k = q * cos + _rotate_half(q) * sin, k * cos + _rotate_half(k) * sin
+        g = self.num_key_value_groups
+        if g > 1:
+            k = k[:, :, None].expand(B, k.shape[1], g, T, d).reshape(B, -1, T, d)
+            v = v[:, :, None].expand(B, v.shape[1], g, T, d).reshape(B, -1, T, d)
+        if attention_mask is None:
+            out = F.scaled_dot_product_attention(q, k, v, is_causal=T > 1)
+        else:
+            m = attention_mask.bool()[:, None, None, :] & torch.ones(T, T, dtype=torch.bool, device=q.device).tril()[None, None]
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=m)
+        return self.o_proj(out.transpose(1, 2).reshape(B, T, -1)), None
+
+
+class MLP(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.gate_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.up_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
+
+    def forward(self, x):
+        return self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x))
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, cfg, layer_idx):
+        super().__init__()
+        self.self_attn = Attention(cfg, layer_idx)
+        self.mlp = MLP(cfg)
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+
+    def forward(self, x, position_embeddings, attention_mask):
+        a, *_ = self.self_attn(hidden_states=self.input_layernorm(x), position_embeddings=position_embeddings,
+                               attention_mask=attention_mask)
+        x = x + a
+        return x + self.mlp(self.post_attention_layernorm(x))
+
+
+class TextModel(nn.Module):
+    def __init__(self, cfg: DecoderConfig):
+        super().__init__()
+        self.config = cfg
+        self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size)
+        self.layers = nn.ModuleList(DecoderLayer(cfg, i) for i in range(cfg.num_hidden_layers))
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+
+    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, position_ids=None):
+        x = self.embed_tokens(input_ids) if inputs_embeds is None else inputs_embeds
+        B, T, _ = x.shape
+        if position_ids is None:
+            position_ids = torch.arange(T, device=x.device)[None].expand(B, T)
+        pe = rope_cos_sin(position_ids, self.config.head_dim, self.config.rope_theta, x.dtype)
+        for layer in self.layers:
+            x = layer(x, pe, attention_mask)
+        return self.norm(x)
+
+
+class _Holder(nn.Module):
+    pass
+
+
+class SyntheticLM(nn.Module):
+    """Top-level module whose `named_modules()` match the reference regexes of `family`."""
+
+    def __init__(self, family: str, cfg: DecoderConfig):
+        super().__init__()
+        self.family, self.config = family, cfg
+        text = TextModel(cfg)
+        if family == "idefics2-8b":
+            self.model = _Holder()
+            self.model.text_model = text                     # model.text_model.layers.N.*
+        elif family == "idefics-9b":
+            self.model = text                                # model.layers.N.*
+        elif family.startswith("llava-interleave"):
+            self.language_model = _Holder()
+            self.language_model.model = text                 # language_model.model.layers.N.*
+        else:
+            raise ValueError(family)
+        self._text = [text]                                  # not a registered child under a second name
+        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
+
+    @property
+    def text(self) -> TextModel:
+        return self._text[0]
+
+    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, position_ids=None,
+                logits_to_keep: int = 0, **kwargs):
+        h = self.text(input_ids=input_ids, inputs_embeds=inputs_embeds, attention_mask=attention_mask,
+                      position_ids=position_ids)
+        hk = h[:, -logits_to_keep:] if logits_to_keep else h          # HF semantics: 0 = all positions
+        return {"logits": self.lm_head(hk), "last_hidden_state": h}
+
+
+def build_synthetic(preset: str, *, dtype=torch.bfloat16, device="cuda", seed: int = 3407, num_layers: Optional[int] = None,
+                    **overrides):
+    """Random-init (N(0, 0.02), seed 3407 like the reference's pl.seed_everything, train.py:85) frozen
+    backbone + the `model_name` the encoder keys on.  Returns (SyntheticLM, model_name)."""
+    model_name, kw = PRESETS[preset]
+    kw = dict(kw, **overrides)
+    if num_layers is not None:
+        kw["num_hidden_layers"] = num_layers
+    cfg = DecoderConfig(**kw)
+    family = "idefics2-8b" if preset == "tiny" else preset
+    with torch.device(device):
+        model = SyntheticLM(family if not family.startswith("llava") else "llava-interleave", cfg).to(dtype)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, cfg.initializer_range, generator=gen)
+            elif "norm" in name:
+                p.fill_(1.0)
+            else:
+                p.zero_()
+    model.requires_grad_(False)
+    return model, model_name
+
+
+class SyntheticTokenizer:
+    pad_token_id, bos_token_id, eos_token_id, padding_side = 0, 1, 2, "left"
+    pad_token, eos_token = "<pad>", "</s>"
+
+
+def synthetic_processor():
+    return types.SimpleNamespace(tokenizer=SyntheticTokenizer())
+
+
+def synthetic_batch(B: int, S_ctx: int, T_q: int, vocab: int, *, seed: int = 3407, max_left_pad: int = 16,
+                    n_answer: int = 4, device="cpu"):
+    """VQAv2-like token batch: full = [pad..][bos] ICE [PAD] query [PAD] answer [eos] (length S_ctx),
+    query-only = [pad..][bos] query [PAD] answer [eos] (length T_q); per-sample 0..max_left_pad left pads
+    (exercises the padding path); ids are random in [3, vocab).  Returns (full_ids, query_ids) int64."""
+    g = torch.Generator().manual_seed(seed)
+    tok = SyntheticTokenizer
+    full = torch.full((B, S_ctx), tok.pad_token_id, dtype=torch.int64)
+    qa = torch.full((B, T_q), tok.pad_token_id, dtype=torch.int64)
+    for i in range(B):
+        lp = int(torch.randint(0, max_left_pad + 1, (1,), generator=g)) if max_left_pad > 0 else 0
+        if i == 0:
+            lp = 0                                            # at least one unpadded row
+        n_q = T_q - lp - 1 - 1 - n_answer - 1                 # bos, PAD, answer, eos
+        n_ice = S_ctx - lp - 1 - 1 - n_q - 1 - n_answer - 1
+        assert n_q > 0 and n_ice > 0
+        ice = torch.randint(3, vocab, (n_ice,), generator=g)
+        query = torch.randint(3, vocab, (n_q,), generator=g)
+        ans = torch.randint(3, vocab, (n_answer,), generator=g)
+        pad, bos, eos = (torch.tensor([x]) for x in (tok.pad_token_id, tok.bos_token_id, tok.eos_token_id))
+        full[i, lp:] = torch.cat([bos, ice, pad, query, pad, ans, eos])
+        qa[i, lp:] = torch.cat([bos, query, pad, ans, eos])
+    return full.to(device), qa.to(device)

@@ -22,6 +22,42 @@ def _count(n: int) -> None:
     launch_count += n
 
 
+class KernelTimer:
+    """Optional CUDA-event brackets around every C-ABI call, on the launching stream (bench.py uses
+    them to report per-kernel device time inside the timed region)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = {}
+
+    def start(self, key):
+        if not self.enabled:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.records.setdefault(key, []).append((a, b))
+        return b
+
+    @staticmethod
+    def stop(ev):
+        if ev is not None:
+            ev.record()
+
+    def summary(self):
+        """key -> (launches, mean ms, total ms); call after a device synchronize."""
+        out = {}
+        for k, evs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[k] = (len(ms), sum(ms) / len(ms), sum(ms))
+        return out
+
+    def reset(self):
+        self.records = {}
+
+
+timer = KernelTimer()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -73,9 +109,11 @@ def shifted_attention_forward(q, k, v, key_mask, shift, w, bias, *, causal, acti
     if active:
         shift, w, bias = (t.float().contiguous() for t in (shift, w, bias))
     desc = _make_desc(q, k, v, out, scale, causal, active, impl)
+    _ev = timer.start(f"attn_fwd_{'active' if active else 'inactive'}_T{T}_S{k.shape[2]}")
     check(lib.mimic_shifted_attn_fwd(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w),
                                      _ptr(bias), _ptr(out), _ptr(lse_c), _ptr(lse_full), _ptr(mu), _stream()),
           "mimic_shifted_attn_fwd")
+    timer.stop(_ev)
     _count(1)
     return out, lse_c, lse_full, mu, (q, k, v, key_mask, shift, w, bias)
 
@@ -98,11 +136,13 @@ def shifted_attention_backward(saved, out, d_out, lse_c, lse_full, mu, *, causal
     desc = _make_desc(q, k, v, out, scale, causal, active, impl)
     nbytes = lib.mimic_shifted_attn_bwd_workspace(desc)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    _ev = timer.start(f"attn_bwd_{'active' if active else 'inactive'}_T{T}_S{k.shape[2]}")
     check(lib.mimic_shifted_attn_bwd(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w), _ptr(bias),
                                      _ptr(out), _ptr(d_out), d_out.stride(0), d_out.stride(1), d_out.stride(2),
                                      _ptr(lse_c), _ptr(lse_full), _ptr(mu), _ptr(dq), _ptr(dk), _ptr(dv),
                                      _ptr(dshift), _ptr(dw), _ptr(dbias), _ptr(ws), nbytes, _stream()),
           "mimic_shifted_attn_bwd")
+    timer.stop(_ev)
     _count(3)
     return dq, dk, dv, dshift, dw, dbias
 
@@ -166,8 +206,10 @@ def record_gather(src: torch.Tensor, src_row: torch.Tensor, dst: torch.Tensor) -
         src2 = src2.contiguous()
     N = src_row.numel()
     assert dst.shape == (N, D) and dst.is_contiguous() and src_row.dtype == torch.int32
+    _ev = timer.start("record_gather")
     check(lib.mimic_record_gather(_ptr(src2), src2.stride(0), _DT[src2.dtype], _ptr(src_row), _ptr(dst), _DT[dst.dtype],
                                   N, D, _stream()), "mimic_record_gather")
+    timer.stop(_ev)
     _count(1)
 
 
@@ -191,9 +233,11 @@ class _AlignMSE(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         nbytes = lib.mimic_mse_workspace(L, rows, D)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _ev = timer.start("mse_fwd_bwd")
         check(lib.mimic_mse_fwd_bwd(ptr_t.data_ptr(), D, _DT[h0.dtype], _ptr(hp), _DT[hp.dtype], _ptr(row_to_compact),
                                     _ptr(row_w), (ptr_t.data_ptr() + 8 * L) if need_grad else None, float(grad_scale),
                                     L, rows, N, D, _ptr(loss), _ptr(ws), nbytes, _stream()), "mimic_mse_fwd_bwd")
+        timer.stop(_ev)
         _count(2)
         ctx.dh = dh
         ctx.shapes = [h.shape for h in hs]
@@ -237,8 +281,10 @@ class _CELoss(torch.autograd.Function):
             dlog = lg if inplace else torch.empty_like(lg)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         n_kept = torch.empty(1, dtype=torch.int32, device=dev)
+        _ev = timer.start("ce_fwd_bwd")
         check(lib.mimic_ce_fwd_bwd(_ptr(lg), lg.stride(0), _DT[lg.dtype], _ptr(labels), _ptr(dlog), float(grad_scale),
                                    R, V, _ptr(loss), _ptr(n_kept), _stream()), "mimic_ce_fwd_bwd")
+        timer.stop(_ev)
         _count(2)
         ctx.dlog = dlog
         ctx.shape = logits.shape

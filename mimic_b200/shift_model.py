@@ -168,6 +168,12 @@ class ShiftModel(nn.Module):
             inputs = self.lmm.process_input(images, full_text).to(device=self.device, dtype=self.dtype)
         return self.forward_inputs(inputs, query_inputs)
 
+    def _model_forward_params(self):
+        import inspect
+        if not hasattr(self, "_fwd_params"):
+            self._fwd_params = set(inspect.signature(self.lmm.model.forward).parameters)
+        return self._fwd_params
+
     def _hp_buffer(self, name, L, N, D, dtype, device):
         buf = self._hp_buffers.get(name)
         if buf is None or buf.shape != (L, N, D) or buf.dtype != dtype or buf.device != device:
@@ -208,6 +214,8 @@ class ShiftModel(nn.Module):
                 enc.record_plan = plans
             # step 1: full-context forward, no grad, adapters off (line 225-226); hooks gather H' rows
             enc.key_mask_override = inputs["attention_mask"]
+            if "logits_to_keep" in self._model_forward_params():
+                inputs.setdefault("logits_to_keep", 1)      # prefix logits are only read by LOGITS_KL_DIV
             with torch.no_grad(), getattr(self.lmm.model, "disable_adapter", nullcontext)():
                 self.lmm.model(**inputs)
             enc.record_plan = None

@@ -1,0 +1,120 @@
+"""On-device MimIC step shell: what pl.Trainer + DeepSpeedCPUAdam do around
+`ShiftModel.forward` in the reference (src/train.py:94-111, src/shift_model.py:306-390), rebuilt
+for one process per GPU:
+
+  * all trainable shift parameters live in ONE flat fp32 buffer (parameters are views), gradients
+    in another; the attention backward accumulates its parameter gradients straight into it
+    (ops.GradSink), so the data-parallel exchange is a single NCCL all-reduce of ~1 MB per
+    optimizer step, with the logged loss scalars riding at its tail (sync_dist, shift_model.py:289);
+  * global-norm clip (train.yaml grad_clip_val) + AdamW with the reference's two weight-decay
+    groups ("bias" names -> 0, shift_model.py:307-336) run as two small kernels on the device;
+  * cosine schedule with linear warm-up (get_cosine_schedule_with_warmup, shift_model.py:384-386),
+    gradient accumulation (train.yaml accumulate_grad_batches).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .shift_model import ShiftModel
+
+
+class FlatShiftParams:
+    def __init__(self, encoder, weight_decay: float, n_scalars: int = 4):
+        named = [(n, p) for n, p in encoder.named_parameters() if p.requires_grad and not n.startswith("lmm")]
+        if not named:
+            raise AssertionError("No parameter to optimize.")
+        dev = named[0][1].device
+        self.names = [n for n, _ in named]
+        self.numel = sum(p.numel() for _, p in named)
+        self.param = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        # gradient buffer + tail slots for the loss scalars (one all-reduce carries both)
+        self.grad_and_scalars = torch.zeros(self.numel + n_scalars, dtype=torch.float32, device=dev)
+        self.grad = self.grad_and_scalars[: self.numel]
+        self.scalars = self.grad_and_scalars[self.numel:]
+        self.weight_decay = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.param)
+        self.exp_avg_sq = torch.zeros_like(self.param)
+        self.views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for n, p in named:
+            k = p.numel()
+            self.param[off:off + k].copy_(p.detach().reshape(-1).float())
+            p.data = self.param[off:off + k].view(p.shape)
+            g = self.grad[off:off + k].view(p.shape)
+            p.grad = g
+            self.views[n] = g
+            self.weight_decay[off:off + k] = 0.0 if "bias" in n else weight_decay      # shift_model.py:309
+            off += k
+        # per-layer sinks for the fused attention backward
+        if hasattr(encoder, "attn_shift") and hasattr(encoder, "log_Z1_lin") and encoder._fused_ok():
+            gs = self.views["attn_shift"]
+            encoder.grad_sinks = [
+                ops.GradSink(gs[l], self.views[f"log_Z1_lin.{l}.weight"], self.views[f"log_Z1_lin.{l}.bias"])
+                for l in range(encoder.lmm_layers)]
+
+
+def cosine_with_warmup(step: int, warmup: int, total: int) -> float:
+    """transformers.get_cosine_schedule_with_warmup lambda (num_cycles 0.5)."""
+    if step < warmup:
+        return step / max(1, warmup)
+    prog = (step - warmup) / max(1, total - warmup)
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+
+
+class MimicTrainer:
+    def __init__(self, shift_model: ShiftModel, *, lr: float = 5e-3, weight_decay: float = 1e-3, warmup_step=0.1,
+                 total_steps: int = 1000, grad_clip_val: float = 1.0, accumulate_grad_batches: int = 1,
+                 process_group=None):
+        self.sm = shift_model
+        self.sm.check_separators = False            # no host sync inside the step
+        self.flat = FlatShiftParams(shift_model.shift_encoder, weight_decay)
+        self.base_lr, self.total_steps = lr, total_steps
+        self.warmup = int(warmup_step * total_steps) if isinstance(warmup_step, float) else int(warmup_step)
+        self.clip = grad_clip_val
+        self.accum = accumulate_grad_batches
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = self.flat.param.device
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.opt_step = 0
+        self.micro = 0
+
+    def micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
+        """One micro-batch: forward (2 passes) + backward.  Steps the optimizer every `accum` calls."""
+        if self.micro % self.accum == 0:
+            self.flat.grad_and_scalars.zero_()
+        loss_dict = self.sm.forward_inputs(inputs, query_inputs, fold_scale=1.0 / self.accum)
+        (loss_dict["loss"] / self.accum).backward()
+        for i, key in enumerate(("loss", "ce_loss", "ffn_mse_loss")):
+            if key in loss_dict:
+                self.flat.scalars[i] += loss_dict[key].detach().float() / self.accum
+        self.micro += 1
+        if self.micro % self.accum == 0:
+            self.optimizer_step()
+        return loss_dict
+
+    def optimizer_step(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad_and_scalars, group=self.pg)      # the only collective of the path
+        self.opt_step += 1
+        lr = self.base_lr * cosine_with_warmup(self.opt_step - 1, self.warmup, self.total_steps)
+        self.lr_dev.fill_(lr)
+        ops.adamw_step(self.flat.param, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq,
+                       self.flat.weight_decay, self.lr_dev, self.opt_step, grad_mul=1.0 / self.world,
+                       max_norm=self.clip, sumsq=self.sumsq)
+
+    def logged_scalars(self) -> Dict[str, float]:
+        """Mean over ranks of the loss terms of the last optimizer step (one D2H read)."""
+        vals = (self.flat.scalars / self.world).tolist()
+        return dict(zip(("loss", "ce_loss", "ffn_mse_loss"), vals))
+
+    # encoder.pth, same keys as the reference's save_pretrained (src/utils.py:96-102)
+    def state_dict_for_checkpoint(self):
+        enc = self.sm.shift_encoder
+        return {k: v.detach().clone() for k, v in enc.state_dict().items() if not k.startswith("lmm")}

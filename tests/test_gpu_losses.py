@@ -64,7 +64,8 @@ def test_align_mse_matches_oracle(dtype, shape):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     for a, b in zip(grads, wg):
         assert rel(a, b) < tol
-        assert float(a[~mask.cuda()].abs().max()) == 0.0          # grad lands only on selected rows
+        if not bool(mask.all()):
+            assert float(a[~mask.cuda()].abs().max()) == 0.0      # grad lands only on selected rows
     # folded upstream scale
     hs_c2 = [h.cuda().requires_grad_(True) for h in hs]
     loss2 = ops.align_mse(hs_c2, hp.cuda(), r2c, w_rows, grad_scale=0.25, assume_folded=True)
