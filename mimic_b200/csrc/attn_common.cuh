@@ -28,6 +28,8 @@ struct AttnParams {
 namespace simt {
 int fwd(const AttnParams& p, cudaStream_t st);
 int bwd(const AttnParams& p, cudaStream_t st);
+int bwd_prep_bf16_d128(const AttnParams& p, cudaStream_t st);   // Delta', dz, dq seed, parameter gradients
+int convert_dq_bf16(const AttnParams& p, cudaStream_t st);      // fp32 dq accumulator -> bf16 dq
 }  // namespace simt
 
 namespace tc {

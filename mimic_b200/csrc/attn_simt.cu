@@ -517,6 +517,21 @@ int launch_bwd(const AttnParams& p, cudaStream_t st) {
   set_error("shifted attention (simt): head_dim %d unsupported (32, 64, 128)", p.d);         \
   return MIMIC_ERR_UNSUPPORTED;
 
+// pieces of the backward that the tcgen05 path shares (bf16, d = 128)
+int bwd_prep_bf16_d128(const AttnParams& p, cudaStream_t st) {
+  dim3 grid((p.T + 63) / 64, p.H, p.B);
+  attn_bwd_prep_kernel<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p);
+  MIMIC_LAUNCH_OK("attn_bwd_prep_kernel");
+  return MIMIC_OK;
+}
+int convert_dq_bf16(const AttnParams& p, cudaStream_t st) {
+  const int64_t n8 = (int64_t)p.B * p.H * p.T * p.d / 8;
+  int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)num_sms() * 8);
+  convert_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p.dq_acc, reinterpret_cast<__nv_bfloat16*>(p.dq), n8);
+  MIMIC_LAUNCH_OK("convert_dq_kernel");
+  return MIMIC_OK;
+}
+
 int fwd(const AttnParams& p, cudaStream_t st) { MIMIC_DISPATCH_SIMT(launch_fwd) }
 int bwd(const AttnParams& p, cudaStream_t st) { MIMIC_DISPATCH_SIMT(launch_bwd) }
 

@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "attn_common.cuh"
+#include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
 namespace mimic {
@@ -388,58 +389,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 // host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// [B, Hn, R, 128] bf16 tensor with element strides (sb, sh, sr, 1) -> 4-D map, box = 64 cols x 128 rows
-static int make_map(CUtensorMap* m, const void* base, int B, int Hn, int R, int64_t sb, int64_t sh, int64_t sr) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return MIMIC_ERR_CUDA;
-  }
-  cuuint64_t dims[4] = {(cuuint64_t)HD, (cuuint64_t)R, (cuuint64_t)Hn, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)sr * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-  // a size-1 dimension may carry any stride; TMA wants non-zero multiples of 16 bytes
-  for (int i = 0; i < 3; ++i)
-    if (strides[i] == 0) strides[i] = (cuuint64_t)HD * 2;
-  cuuint32_t box[4] = {64, 128, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (R=%d Hn=%d B=%d strides %lld %lld %lld)", (int)r, R, Hn, B,
-              (long long)sr, (long long)sh, (long long)sb);
-    return MIMIC_ERR_CUDA;
-  }
-  return MIMIC_OK;
-}
-
 bool supports(const AttnParams& p, bool backward) {
-  if (backward) return false;   // tcgen05 backward lands separately
+  (void)backward;
   return p.dtype == MIMIC_BF16 && p.d == HD && p.S <= (1 << 18) && p.T >= 1;
 }
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st))) return rc;
-  if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss))) return rc;
-  if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss))) return rc;
+  if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, 128))) return rc;
+  if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, 128))) return rc;
+  if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, 128))) return rc;
   const size_t smem = FwdSmem::bytes(p.S);
   static size_t configured = 0;
   if (smem > configured) {
@@ -450,11 +410,6 @@ int fwd(const AttnParams& p, cudaStream_t st) {
   attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tk, tv, p);
   MIMIC_LAUNCH_OK("attn_fwd_tc_kernel");
   return MIMIC_OK;
-}
-
-int bwd(const AttnParams&, cudaStream_t) {
-  set_error("tcgen05 backward not built");
-  return MIMIC_ERR_UNSUPPORTED;
 }
 
 }  // namespace tc

@@ -1,0 +1,378 @@
+// Shifted self-attention BACKWARD on Blackwell tensor cores (bf16, head_dim 128).
+// Math: SURVEY.md Appendix A (backward of SDPA + do_shift, src/shift_encoder.py:352-359, 682-732).
+//
+// One CTA per (128-key tile, kv head, batch); it keeps K and V resident in shared memory, walks the
+// query heads of the GQA group and their 64-row query tiles, and accumulates dK, dV in TMEM:
+//
+//   S^T  = K Q_i^T      SS mma, M=128 keys, N=64 queries   -> TMEM SdQ[i&1]       (keys on TMEM lanes)
+//   dP^T = V dO_i^T     SS mma                              -> TMEM dP[i&1]        (causal tiles only)
+//   softmax warps (one key row per thread, 64 query columns):
+//        P^T  = exp2(s - lse_c[t])            visible entries
+//        dS^T = P^T (dP^T - Delta'[t])        visible;   -dz[t] exp2(s - lse_full[t])   excluded (future/masked)
+//        -> bf16 P^T, dS^T back into TMEM (A operands) and dS^T into smem ([keys][queries], B operand)
+//   dV  += P^T dO_i     TS mma (A from TMEM, B = dO_i MN-major)           (causal tiles only)
+//   dK  += dS^T Q_i     TS mma
+//   dQ^T = K^T dS^T     SS mma, M=128 (d), N=64 queries (A = K MN-major, B = dS^T MN-major) -> TMEM SdQ[i&1]
+//   drain warps: dQ^T TMEM -> registers -> fp32 smem [64][128] -> ONE bulk reduce-add
+//        (cp.reduce.async.bulk .add.f32) into the fp32 dq accumulator — no per-element atomics.
+// Delta' folds the visible part of the shift term: Delta' = g.SA + dz exp(lse_c - lse_full) (prep kernel).
+// TMEM map (512 cols): dV [0,128) dK [128,256) SdQ0 [256,320) SdQ1 [320,384) dP0 [384,448) dP1 [448,512).
+#include <cuda.h>
+
+#include "attn_common.cuh"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace mimic {
+namespace tc {
+
+using namespace ptx;
+
+namespace bw {
+constexpr int BN = 128;                    // keys per CTA
+constexpr int BQ = 64;                     // queries per iteration
+constexpr int HD = 128;
+constexpr int KV_HALF = 128 * 128;         // [128 keys][128 B]
+constexpr int KV_TILE = 2 * KV_HALF;       // 32 KB
+constexpr int Q_HALF = BQ * 128;           // [64 rows][128 B] = 8 KB
+constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
+constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
+constexpr int STAGE_BYTES = BQ * HD * 4;   // fp32 dQ staging, 32 KB
+constexpr int THREADS = 320;
+constexpr float LOG2E = 1.4426950408889634f;
+
+constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + 2 * Q_TILE, OFF_DS = OFF_DO + 2 * Q_TILE,
+              OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 2 * BQ * 16,
+              OFF_TMEM = OFF_BAR + 16 * 8, SMEM_BYTES = OFF_TMEM + 16 + 1024;
+
+enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, S_FULL = 5, SOFT_DONE = 7, DQ_FULL = 9, DRAIN_DONE = 11, DKV_FULL = 13, N_BARS = 14 };
+
+constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_SDQ = 256, TM_DP = 384;
+constexpr uint32_t IDESC_ST = idesc_bf16(128, BQ, 0, 0);     // S^T, dP^T : A, B K-major
+constexpr uint32_t IDESC_DKV = idesc_bf16(128, HD, 0, 1);    // dV, dK    : A in TMEM, B MN-major
+constexpr uint32_t IDESC_DQT = idesc_bf16(128, BQ, 1, 1);    // dQ^T      : A = K MN-major, B = dS^T MN-major
+}  // namespace bw
+
+__device__ __forceinline__ uint32_t low_bits_b(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+__global__ void __launch_bounds__(bw::THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnParams p) {
+  using namespace bw;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + OFF_K;
+  uint8_t* sV = smem + OFF_V;
+  uint8_t* sQ = smem + OFF_Q;
+  uint8_t* sDO = smem + OFF_DO;
+  uint8_t* sDS = smem + OFF_DS;
+  float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
+  float4* stats = reinterpret_cast<float4*>(smem + OFF_STATS);      // [2][64] (lse_c*log2e, Delta', dz, lse_full*log2e)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.Hkv;
+  const int T = p.T, S = p.S, off = p.S - p.T;
+  const int s0 = kt * BN;
+  const int n_qt = (T + BQ - 1) / BQ;
+  int qt_first = 0;
+  if (!p.active && p.causal) {
+    const int tmin = s0 - off;                         // first query row that can see key s0
+    qt_first = tmin <= 0 ? 0 : tmin / BQ;
+  }
+  const int nq = n_qt - qt_first;                      // query tiles per head (>= 1 for every key tile in range)
+  const int n = nq > 0 ? G * nq : 0;                   // iterations
+  auto need_c = [&](int qt) { return !p.causal || (min(qt * BQ + BQ - 1, T - 1) + off >= s0); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(&bars[KV_FULL], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars[QDO_FULL + i], 1);
+        mbar_init(&bars[QDO_EMPTY + i], 1);
+        mbar_init(&bars[S_FULL + i], 1);
+        mbar_init(&bars[SOFT_DONE + i], 128);
+        mbar_init(&bars[DQ_FULL + i], 1);
+        mbar_init(&bars[DRAIN_DONE + i], 128);
+      }
+      mbar_init(&bars[DKV_FULL], 1);
+      fence_barrier_init();
+      prefetch_tmap(&tm_q);
+      prefetch_tmap(&tm_k);
+      prefetch_tmap(&tm_v);
+      prefetch_tmap(&tm_do);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(&bars[KV_FULL], 2 * KV_TILE);
+      tma_load_4d(sK, &tm_k, &bars[KV_FULL], 0, s0, kvh, b);
+      tma_load_4d(sK + KV_HALF, &tm_k, &bars[KV_FULL], 64, s0, kvh, b);
+      tma_load_4d(sV, &tm_v, &bars[KV_FULL], 0, s0, kvh, b);
+      tma_load_4d(sV + KV_HALF, &tm_v, &bars[KV_FULL], 64, s0, kvh, b);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1;
+        const int h = kvh * G + i / nq, qt = qt_first + i % nq;
+        const bool nc = need_c(qt);
+        mbar_wait(&bars[QDO_EMPTY + st], ((i >> 1) & 1) ^ 1, 100 + st);
+        mbar_expect_tx(&bars[QDO_FULL + st], nc ? 2 * Q_TILE : Q_TILE);
+        tma_load_4d(sQ + st * Q_TILE, &tm_q, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
+        tma_load_4d(sQ + st * Q_TILE + Q_HALF, &tm_q, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
+        if (nc) {
+          tma_load_4d(sDO + st * Q_TILE, &tm_do, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
+          tma_load_4d(sDO + st * Q_TILE + Q_HALF, &tm_do, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n > 0) {
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO),
+                     ds_addr = smem_u32(sDS);
+      mbar_wait(&bars[KV_FULL], 0, 200);
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        const int qt = qt_first + i % nq;
+        mbar_wait(&bars[QDO_FULL + st], (i >> 1) & 1, 210 + st);
+        mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
+          mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + ko_kv, 16, 1024),
+                 smem_desc_sw128(q_addr + st * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
+        }
+        if (need_c(qt)) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
+            mma_ss(tmem_base + TM_DP + st * BQ, smem_desc_sw128(v_addr + ko_kv, 16, 1024),
+                   smem_desc_sw128(do_addr + st * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
+          }
+        }
+        tc_commit(&bars[S_FULL + st]);
+      };
+      bool dv_started = false;
+      issue_sdp(0);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1;
+        const int qt = qt_first + i % nq;
+        if (i + 1 < n) issue_sdp(i + 1);
+        mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
+        tc_fence_after();
+        if (need_c(qt)) {
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k)       // dV += P^T dO_i : K = 16 queries per step (8 TMEM cols; 2 KB of dO rows)
+            mma_ts(tmem_base + TM_DV, tmem_base + TM_SDQ + st * BQ + k * 8,
+                   smem_desc_sw128(do_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (dv_started || k > 0));
+          dv_started = true;
+        }
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)         // dK += dS^T Q_i
+          mma_ts(tmem_base + TM_DK, tmem_base + TM_DP + st * BQ + k * 8,
+                 smem_desc_sw128(q_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (i > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k)         // dQ^T = K^T dS^T : K = 16 keys per step
+          mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + k * 2048, KV_HALF, 1024),
+                 smem_desc_sw128(ds_addr + st * DS_TILE + k * 2048, 16, 1024), IDESC_DQT, k > 0);
+        tc_commit(&bars[QDO_EMPTY + st]);
+        tc_commit(&bars[DQ_FULL + st]);
+      }
+      tc_commit(&bars[DKV_FULL]);
+    }
+  } else if (warp < 6) {
+    // ===================== softmax warps: one key row per thread =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int s = s0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float scale2 = p.scale * LOG2E;
+    const int sid = threadIdx.x - 64;                   // 0..127 inside the softmax group
+    const bool key_in = s < S;
+    const bool key_ok = key_in && (p.key_mask == nullptr || p.key_mask[(int64_t)b * S + s] != 0);
+
+    auto load_stats = [&](int i, float4& v) {          // threads 0..63 of the group: column sid of iteration i
+      const int h = kvh * G + i / nq, qt = qt_first + i % nq;
+      const int t = qt * BQ + sid;
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T) {
+        const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
+        v.x = p.lse_c[ridx] * LOG2E;
+        v.y = p.delta_ws[ridx];
+        v.z = p.dz_ws[ridx];
+        v.w = p.active ? p.lse_full[ridx] * LOG2E : 0.f;
+      }
+    };
+    float4 nxt;
+    if (n > 0 && sid < BQ) {
+      load_stats(0, nxt);
+      stats[sid] = nxt;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int st = i & 1;
+      const int qt = qt_first + i % nq;
+      const int t0 = qt * BQ;
+      const bool nc = need_c(qt);
+      if (i + 1 < n && sid < BQ) load_stats(i + 1, nxt);        // prefetch next iteration's row statistics
+      named_bar_sync(1, 128);                                   // stats[st] written by everyone; stats[st^1] no longer read
+      mbar_wait(&bars[S_FULL + st], (i >> 1) & 1, 310 + st);
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ;
+      const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ;
+      uint8_t* ds_row = sDS + st * DS_TILE + r * 128;
+      const float4* stt = stats + st * BQ;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        // visibility of queries t0+32*hf+c (c = 0..31) for key s: visible iff s <= t + off
+        const uint32_t trow = low_bits_b(T - t0 - 32 * hf);
+        const uint32_t cz = p.causal ? ~low_bits_b(s - off - t0 - 32 * hf) : 0xFFFFFFFFu;
+        const uint32_t vw = key_ok ? (trow & cz) : 0u;
+        const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
+        float sv[32], dpv[32];
+        tmem_ld32(t_s + 32 * hf, sv);
+        if (nc) tmem_ld32(t_dp + 32 * hf, dpv);
+        tc_wait_ld();
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int c2 = 0; c2 < 16; ++c2) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * c2 + e;
+            const float4 stc = stt[32 * hf + c];
+            const float sc = sv[c] * scale2;
+            float pe = 0.f, de = 0.f;
+            if ((vw >> c) & 1u) {
+              pe = ex2(sc - stc.x);
+              de = pe * ((nc ? dpv[c] : 0.f) - stc.y);
+            } else if ((xw >> c) & 1u) {
+              de = -stc.z * ex2(sc - stc.w);
+            }
+            pv[e] = pe;
+            dsv[e] = de * p.scale;
+          }
+          pk[c2] = pack_bf16(pv[0], pv[1]);
+          dk_[c2] = pack_bf16(dsv[0], dsv[1]);
+        }
+        if (nc) tmem_st16(t_s + 16 * hf, pk);                   // P^T  -> first 32 cols of SdQ[st]
+        tmem_st16(t_dp + 16 * hf, dk_);                         // dS^T -> first 32 cols of dP[st]
+        // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = hf * 4 + ch;
+          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(dk_[4 * ch], dk_[4 * ch + 1], dk_[4 * ch + 2], dk_[4 * ch + 3]);
+        }
+      }
+      if (i + 1 < n && sid < BQ) stats[(st ^ 1) * BQ + sid] = nxt;
+      tc_wait_st();
+      fence_proxy_async();                                      // smem dS^T visible to the tensor-core (async) proxy
+      tc_fence_before();
+      mbar_arrive(&bars[SOFT_DONE + st]);
+    }
+    // ---- epilogue: dK, dV rows (this thread's key) -> global bf16 ----
+    if (n > 0) {
+      mbar_wait(&bars[DKV_FULL], 0, 330);
+      tc_fence_after();
+    }
+    __nv_bfloat16* dkrow = reinterpret_cast<__nv_bfloat16*>(p.dk) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
+    __nv_bfloat16* dvrow = reinterpret_cast<__nv_bfloat16*>(p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        float o[32];
+        if (n > 0) {
+          tmem_ld32(tmem_base + lane_off + (which ? TM_DK : TM_DV) + 32 * i4, o);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = 0.f;
+        }
+        if (key_in) {
+          __nv_bfloat16* dst = (which ? dkrow : dvrow) + 32 * i4;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = o[8 * c8 + e];
+            store8(dst + 8 * c8, f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== drain warps: dQ^T (TMEM, d on lanes) -> smem fp32 [64][128] -> bulk reduce-add =====================
+    const int quarter = warp & 3;
+    const int c = quarter * 32 + lane;                  // head-dim index owned by this thread
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int did = threadIdx.x - 192;                  // 0..127
+    for (int i = 0; i < n; ++i) {
+      const int st = i & 1;
+      const int h = kvh * G + i / nq, qt = qt_first + i % nq;
+      mbar_wait(&bars[DQ_FULL + st], (i >> 1) & 1, 410 + st);
+      tc_fence_after();
+      float v0[32], v1[32];
+      tmem_ld32(tmem_base + lane_off + TM_SDQ + st * BQ, v0);
+      tmem_ld32(tmem_base + lane_off + TM_SDQ + st * BQ + 32, v1);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
+      if (did == 0) bulk_wait_read0();                  // previous bulk reduce finished reading the staging tile
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        stage[t * HD + c] = v0[t];
+        stage[(t + 32) * HD + c] = v1[t];
+      }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (did == 0) {
+        const int rows = min(BQ, T - qt * BQ);
+        float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
+        bulk_reduce_add_f32(gdst, stage, (uint32_t)rows * HD * 4);
+        bulk_commit();
+      }
+    }
+    if (did == 0) bulk_wait0();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int bwd(const AttnParams& p, cudaStream_t st) {
+  using namespace bw;
+  int rc;
+  if ((rc = simt::bwd_prep_bf16_d128(p, st))) return rc;
+  CUtensorMap tq, tk, tv, tdo;
+  if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BQ))) return rc;
+  if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
+  if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, BN))) return rc;
+  if ((rc = make_map(&tdo, p.d_out, p.B, p.H, p.T, p.go_sb, p.go_sh, p.go_st, BQ))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
+  attn_bwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, p);
+  MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
+  return simt::convert_dq_bf16(p, st);
+}
+
+}  // namespace tc
+}  // namespace mimic

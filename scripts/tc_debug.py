@@ -48,6 +48,63 @@ def case(name, B, H, Hkv, T, S, causal, active, pad=False, seed=0, oracle=True):
     return rel(t_[0], a[0])
 
 
+def bcase(name, B, H, Hkv, T, S, causal, active, pad=False, seed=0):
+    """backward: tcgen05 vs simt on the same forward statistics, and vs the oracle."""
+    g = torch.Generator().manual_seed(seed)
+    d = 128
+    q = torch.randn(B, H, T, d, generator=g).bfloat16()
+    k = torch.randn(B, Hkv, S, d, generator=g).bfloat16()
+    v = torch.randn(B, Hkv, S, d, generator=g).bfloat16()
+    do = torch.randn(B, T, H, d, generator=g).bfloat16()
+    shift, w, b = torch.randn(H, d, generator=g) * 0.5, torch.randn(H, d, generator=g) * 0.2, torch.randn(H, generator=g)
+    km = None
+    if pad:
+        km = torch.ones(B, S, dtype=torch.bool)
+        km[0, :5] = False
+        km[B - 1, S // 2] = False
+        vis = OA.visibility(T, S, B, causal, km).any(-1)[:, 0]
+        do = do * vis[:, :, None, None]
+    args = [t.cuda() for t in (q, k, v)]
+    kmc = None if km is None else km.cuda()
+    sh, ww, bb = (shift.cuda(), w.cuda(), b.cuda()) if active else (None, None, None)
+    out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(*args, kmc, sh, ww, bb, causal=causal, active=active,
+                                                                 scale=d ** -0.5, impl="tcgen05")
+    res = {}
+    for impl in ("simt", "tcgen05"):
+        r = ops.shifted_attention_backward(saved, out, do.cuda(), lse_c, lse_f, mu, causal=causal, active=active,
+                                           scale=d ** -0.5, impl=impl)
+        torch.cuda.synchronize()
+        res[impl] = r
+    names = ["dq", "dk", "dv"] + (["dshift", "dw", "db"] if active else [])
+    msg = f"{name:28s} tc-vs-simt " + " ".join(f"{n}={rel(res['tcgen05'][i], res['simt'][i]):.1e}" for i, n in enumerate(names))
+    want = OA.shifted_attention_bwd(q.float(), k.float(), v.float(), shift, w, b, do.float(), causal=causal, key_mask=km, active=active)
+    msg += " | tc-vs-oracle " + " ".join(f"{n}={rel(res['tcgen05'][i], want[n]):.1e}" for i, n in enumerate(names[:3]))
+    print(msg, flush=True)
+
+
+def bperf(B, H, Hkv, T, active, reps=5):
+    d = 128
+    q = torch.randn(B, H, T, d, device="cuda").bfloat16()
+    k = torch.randn(B, Hkv, T, d, device="cuda").bfloat16()
+    v = torch.randn(B, Hkv, T, d, device="cuda").bfloat16()
+    do = torch.randn(B, T, H, d, device="cuda").bfloat16()
+    sh, ww, bb = (torch.randn(H, d, device="cuda") * 0.5, torch.randn(H, d, device="cuda") * 0.2, torch.randn(H, device="cuda")) if active else (None,) * 3
+    out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, None, sh, ww, bb, causal=True, active=active, scale=d ** -0.5, impl="tcgen05")
+    for impl in ("tcgen05",):
+        for _ in range(2):
+            ops.shifted_attention_backward(saved, out, do, lse_c, lse_f, mu, causal=True, active=active, scale=d ** -0.5, impl=impl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.shifted_attention_backward(saved, out, do, lse_c, lse_f, mu, causal=True, active=active, scale=d ** -0.5, impl=impl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        fl = (8 if active else 5) * B * H * T * T * d
+        print(f"bwd perf {impl} B={B} H={H} T={T} active={int(active)}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (prep+main+convert)", flush=True)
+
+
 def perf(B, H, Hkv, T, active, reps=10):
     d = 128
     q = torch.randn(B, H, T, d, device="cuda").bfloat16()
@@ -82,6 +139,20 @@ if __name__ == "__main__":
         case("T<S cache active", 2, 4, 4, 64, 448, True, True, pad=True)
         case("T=1 decode", 2, 4, 2, 1, 300, False, True)
         case("ctx 3200 inactive", 1, 4, 1, 3200, 3200, True, False, oracle=False)
+    if which in ("all", "bwd"):
+        bcase("b 1tile noncausal inactive", 1, 1, 1, 64, 128, False, False)
+        bcase("b 1tile causal inactive", 1, 1, 1, 128, 128, True, False)
+        bcase("b 1tile causal active", 1, 1, 1, 128, 128, True, True)
+        bcase("b 4tile causal active", 1, 2, 2, 512, 512, True, True)
+        bcase("b ragged gqa pad active", 2, 8, 2, 200, 200, True, True, pad=True)
+        bcase("b ragged gqa pad inactive", 2, 8, 2, 333, 333, True, False, pad=True)
+        bcase("b T<S cache active", 2, 4, 4, 64, 448, True, True, pad=True)
+        bcase("b T=1 decode", 2, 4, 2, 1, 300, False, True)
+    if which in ("all", "bperf"):
+        bperf(2, 32, 8, 128, True)
+        bperf(4, 32, 32, 4096, False)
+        bperf(4, 32, 32, 4096, True)
+        bperf(2, 32, 32, 8192, True)
     if which in ("all", "perf"):
         perf(2, 32, 8, 3200, False)
         perf(2, 32, 8, 3200, True)
