@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
     for (int r = 0; r < 64; ++r) {
       const int t = t0 + r;
       if (t >= T) break;
-      p.dq_acc[(row0 + t) * D + c] = dz_s[r] * wv;
+      p.dq_acc[(row0 + t) * D + c] = dz_s[r] * wv * p.dq_seed_mul;
       if (p.active) {
         acc_s += mu_s[r] * to_f32(gb[(int64_t)t * p.go_st + c]);
         acc_w += dz_s[r] * to_f32(qb[(int64_t)t * p.q_st + c]);
@@ -467,10 +467,12 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnParams p) {
 }
 
 template <typename E>
-__global__ void convert_dq_kernel(const float* __restrict__ src, E* __restrict__ dst, int64_t n8) {
+__global__ void convert_dq_kernel(const float* __restrict__ src, E* __restrict__ dst, int64_t n8, float mul) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     float f[8];
     load8(src + i * 8, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= mul;
     store8(dst + i * 8, f);
   }
 }
@@ -499,7 +501,7 @@ int launch_bwd(const AttnParams& p, cudaStream_t st) {
   MIMIC_LAUNCH_OK("attn_bwd_kernel(simt)");
   const int64_t n8 = (int64_t)p.B * p.H * p.T * D / 8;
   int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)num_sms() * 8);
-  convert_dq_kernel<E><<<blocks, 256, 0, st>>>(p.dq_acc, reinterpret_cast<E*>(p.dq), n8);
+  convert_dq_kernel<E><<<blocks, 256, 0, st>>>(p.dq_acc, reinterpret_cast<E*>(p.dq), n8, 1.f);
   MIMIC_LAUNCH_OK("convert_dq_kernel");
   return MIMIC_OK;
 }
@@ -527,7 +529,7 @@ int bwd_prep_bf16_d128(const AttnParams& p, cudaStream_t st) {
 int convert_dq_bf16(const AttnParams& p, cudaStream_t st) {
   const int64_t n8 = (int64_t)p.B * p.H * p.T * p.d / 8;
   int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)num_sms() * 8);
-  convert_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p.dq_acc, reinterpret_cast<__nv_bfloat16*>(p.dq), n8);
+  convert_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p.dq_acc, reinterpret_cast<__nv_bfloat16*>(p.dq), n8, p.dq_out_mul);
   MIMIC_LAUNCH_OK("convert_dq_kernel");
   return MIMIC_OK;
 }

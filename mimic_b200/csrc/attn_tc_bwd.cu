@@ -11,7 +11,7 @@
 //        dS^T = P^T (dP^T - Delta'[t])        visible;   -dz[t] exp2(s - lse_full[t])   excluded (future/masked)
 //        -> bf16 P^T, dS^T back into TMEM (A operands) and dS^T into smem ([keys][queries], B operand)
 //   dV  += P^T dO_i     TS mma (A from TMEM, B = dO_i MN-major)           (causal tiles only)
-//   dK  += dS^T Q_i     TS mma
+//   dK  += dS^T Q_i     TS mma   (dS carries no softmax scale: dK x scale in the epilogue, dQ x scale at conversion)
 //   dQ^T = K^T dS^T     SS mma, M=128 (d), N=64 queries (A = K MN-major, B = dS^T MN-major) -> TMEM SdQ[i&1]
 //   drain warps: dQ^T TMEM -> registers -> fp32 smem [64][128] -> ONE bulk reduce-add
 //        (cp.reduce.async.bulk .add.f32) into the fp32 dq accumulator — no per-element atomics.
@@ -38,7 +38,7 @@ constexpr int Q_HALF = BQ * 128;           // [64 rows][128 B] = 8 KB
 constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
 constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
 constexpr int STAGE_BYTES = BQ * HD * 4;   // fp32 dQ staging, 32 KB
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;                // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM quarter), warps 10-13 drain
 constexpr float LOG2E = 1.4426950408889634f;
 
 constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + 2 * Q_TILE, OFF_DS = OFF_DO + 2 * Q_TILE,
@@ -93,7 +93,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_init(&bars[QDO_FULL + i], 1);
         mbar_init(&bars[QDO_EMPTY + i], 1);
         mbar_init(&bars[S_FULL + i], 1);
-        mbar_init(&bars[SOFT_DONE + i], 128);
+        mbar_init(&bars[SOFT_DONE + i], 256);
         mbar_init(&bars[DQ_FULL + i], 1);
         mbar_init(&bars[DRAIN_DONE + i], 128);
       }
@@ -173,13 +173,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (need_c(qt)) {
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)       // dV += P^T dO_i : K = 16 queries per step (8 TMEM cols; 2 KB of dO rows)
-            mma_ts(tmem_base + TM_DV, tmem_base + TM_SDQ + st * BQ + k * 8,
+            mma_ts(tmem_base + TM_DV, tmem_base + TM_SDQ + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
                    smem_desc_sw128(do_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (dv_started || k > 0));
           dv_started = true;
         }
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k)         // dK += dS^T Q_i
-          mma_ts(tmem_base + TM_DK, tmem_base + TM_DP + st * BQ + k * 8,
+          mma_ts(tmem_base + TM_DK, tmem_base + TM_DP + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
                  smem_desc_sw128(q_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (i > 0 || k > 0));
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)         // dQ^T = K^T dS^T : K = 16 keys per step
@@ -190,16 +190,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       tc_commit(&bars[DKV_FULL]);
     }
-  } else if (warp < 6) {
-    // ===================== softmax warps: one key row per thread =====================
+  } else if (warp < 10) {
+    // ===================== softmax warps: one key row x 32 query columns per thread =====================
+    // warps 2-5 take query columns 0-31 of the tile, warps 6-9 columns 32-63 (two warps per TMEM lane quarter)
     const int quarter = warp & 3;
+    const int hf = warp >= 6 ? 1 : 0;
     const int r = quarter * 32 + lane;
     const int s = s0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float scale2 = p.scale * LOG2E;
-    const int sid = threadIdx.x - 64;                   // 0..127 inside the softmax group
+    const int sid = threadIdx.x - 64;                   // 0..255 inside the softmax group
     const bool key_in = s < S;
     const bool key_ok = key_in && (p.key_mask == nullptr || p.key_mask[(int64_t)b * S + s] != 0);
+    const uint32_t pcol = hf ? 48 : 0;                  // where this half's packed P^T / dS^T columns go
 
     auto load_stats = [&](int i, float4& v) {          // threads 0..63 of the group: column sid of iteration i
       const int h = kvh * G + i / nq, qt = qt_first + i % nq;
@@ -207,10 +210,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t < T) {
         const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
-        v.x = p.lse_c[ridx] * LOG2E;
+        v.x = -p.lse_c[ridx] * LOG2E;                   // negated: exp2(fma(s, scale2, -lse))
         v.y = p.delta_ws[ridx];
-        v.z = p.dz_ws[ridx];
-        v.w = p.active ? p.lse_full[ridx] * LOG2E : 0.f;
+        v.z = -p.dz_ws[ridx];
+        v.w = p.active ? -p.lse_full[ridx] * LOG2E : 0.f;
       }
     };
     float4 nxt;
@@ -224,55 +227,72 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int t0 = qt * BQ;
       const bool nc = need_c(qt);
       if (i + 1 < n && sid < BQ) load_stats(i + 1, nxt);        // prefetch next iteration's row statistics
-      named_bar_sync(1, 128);                                   // stats[st] written by everyone; stats[st^1] no longer read
+      named_bar_sync(1, 256);                                   // stats[st] complete; stats[st^1] no longer read
       mbar_wait(&bars[S_FULL + st], (i >> 1) & 1, 310 + st);
       tc_fence_after();
       const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ;
       const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ;
       uint8_t* ds_row = sDS + st * DS_TILE + r * 128;
-      const float4* stt = stats + st * BQ;
+      const float4* stt = stats + st * BQ + 32 * hf;
+      // visibility of queries t0+32*hf+c (c = 0..31) for key s: visible iff s <= t + off
+      const uint32_t trow = low_bits_b(T - t0 - 32 * hf);
+      const uint32_t cz = p.causal ? ~low_bits_b(s - off - t0 - 32 * hf) : 0xFFFFFFFFu;
+      const uint32_t vw = key_ok ? (trow & cz) : 0u;
+      const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
+      float sv[32], dpv[32];
+      tmem_ld32(t_s + 32 * hf, sv);
+      if (nc) tmem_ld32(t_dp + 32 * hf, dpv);
+      tc_wait_ld();
+      uint32_t pk[16], dk_[16];
+      const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFFFFFu);
+      const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFFFFFu);
+      if (all_v && nc) {
+        // interior causal tile: every entry visible.  dS (unscaled) = P (dP - Delta'); scale is applied to dK / dQ later
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        // visibility of queries t0+32*hf+c (c = 0..31) for key s: visible iff s <= t + off
-        const uint32_t trow = low_bits_b(T - t0 - 32 * hf);
-        const uint32_t cz = p.causal ? ~low_bits_b(s - off - t0 - 32 * hf) : 0xFFFFFFFFu;
-        const uint32_t vw = key_ok ? (trow & cz) : 0u;
-        const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
-        float sv[32], dpv[32];
-        tmem_ld32(t_s + 32 * hf, sv);
-        if (nc) tmem_ld32(t_dp + 32 * hf, dpv);
-        tc_wait_ld();
-        uint32_t pk[16], dk_[16];
+        for (int c2 = 0; c2 < 16; ++c2) {
+          const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
+          const float p0 = ex2(fmaf(sv[2 * c2], scale2, a.x)), p1 = ex2(fmaf(sv[2 * c2 + 1], scale2, bq.x));
+          pk[c2] = pack_bf16(p0, p1);
+          dk_[c2] = pack_bf16(p0 * (dpv[2 * c2] - a.y), p1 * (dpv[2 * c2 + 1] - bq.y));
+        }
+      } else if (all_x) {
+        // tile above the diagonal (shift term only): dS = -dz exp2(s - lse_full)
+#pragma unroll
+        for (int c2 = 0; c2 < 16; ++c2) {
+          const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
+          pk[c2] = 0u;
+          dk_[c2] = pack_bf16(a.z * ex2(fmaf(sv[2 * c2], scale2, a.w)), bq.z * ex2(fmaf(sv[2 * c2 + 1], scale2, bq.w)));
+        }
+      } else {
 #pragma unroll
         for (int c2 = 0; c2 < 16; ++c2) {
           float pv[2], dsv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = 2 * c2 + e;
-            const float4 stc = stt[32 * hf + c];
-            const float sc = sv[c] * scale2;
+            const float4 stc = stt[c];
             float pe = 0.f, de = 0.f;
             if ((vw >> c) & 1u) {
-              pe = ex2(sc - stc.x);
+              pe = ex2(fmaf(sv[c], scale2, stc.x));
               de = pe * ((nc ? dpv[c] : 0.f) - stc.y);
             } else if ((xw >> c) & 1u) {
-              de = -stc.z * ex2(sc - stc.w);
+              de = stc.z * ex2(fmaf(sv[c], scale2, stc.w));
             }
             pv[e] = pe;
-            dsv[e] = de * p.scale;
+            dsv[e] = de;
           }
           pk[c2] = pack_bf16(pv[0], pv[1]);
           dk_[c2] = pack_bf16(dsv[0], dsv[1]);
         }
-        if (nc) tmem_st16(t_s + 16 * hf, pk);                   // P^T  -> first 32 cols of SdQ[st]
-        tmem_st16(t_dp + 16 * hf, dk_);                         // dS^T -> first 32 cols of dP[st]
-        // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
+      }
+      if (nc) tmem_st16(t_s + pcol, pk);                        // P^T  (A operand of dV)
+      tmem_st16(t_dp + pcol, dk_);                              // dS^T (A operand of dK)
+      // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = hf * 4 + ch;
-          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(dk_[4 * ch], dk_[4 * ch + 1], dk_[4 * ch + 2], dk_[4 * ch + 3]);
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = hf * 4 + ch;
+        *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(dk_[4 * ch], dk_[4 * ch + 1], dk_[4 * ch + 2], dk_[4 * ch + 3]);
       }
       if (i + 1 < n && sid < BQ) stats[(st ^ 1) * BQ + sid] = nxt;
       tc_wait_st();
@@ -280,15 +300,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
     }
-    // ---- epilogue: dK, dV rows (this thread's key) -> global bf16 ----
+    // ---- epilogue: warps 2-5 write this key's dV row, warps 6-9 its dK row (x softmax scale) ----
     if (n > 0) {
       mbar_wait(&bars[DKV_FULL], 0, 330);
       tc_fence_after();
     }
-    __nv_bfloat16* dkrow = reinterpret_cast<__nv_bfloat16*>(p.dk) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
-    __nv_bfloat16* dvrow = reinterpret_cast<__nv_bfloat16*>(p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = hf;                              // 0: dV, 1: dK
+      const float mul = which ? p.scale : 1.f;
+      __nv_bfloat16* dst0 = reinterpret_cast<__nv_bfloat16*>(which ? p.dk : p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) {
         float o[32];
@@ -300,13 +320,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           for (int c = 0; c < 32; ++c) o[c] = 0.f;
         }
         if (key_in) {
-          __nv_bfloat16* dst = (which ? dkrow : dvrow) + 32 * i4;
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = o[8 * c8 + e];
-            store8(dst + 8 * c8, f);
+            for (int e = 0; e < 8; ++e) f[e] = o[8 * c8 + e] * mul;
+            store8(dst0 + 32 * i4 + 8 * c8, f);
           }
         }
       }
@@ -317,7 +336,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int quarter = warp & 3;
     const int c = quarter * 32 + lane;                  // head-dim index owned by this thread
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int did = threadIdx.x - 192;                  // 0..127
+    const int did = threadIdx.x - 320;                  // 0..127
     for (int i = 0; i < n; ++i) {
       const int st = i & 1;
       const int h = kvh * G + i / nq, qt = qt_first + i % nq;
@@ -357,7 +376,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 int bwd(const AttnParams& p, cudaStream_t st) {
   using namespace bw;
   int rc;
-  if ((rc = simt::bwd_prep_bf16_d128(p, st))) return rc;
+  // the softmax scale is NOT applied to dS in the main kernel: dK is scaled in its epilogue, dQ in the
+  // fp32 -> bf16 conversion; the dq seed (dz * w) is pre-divided so that it comes out unscaled
+  AttnParams pp = p;
+  pp.dq_seed_mul = 1.f / p.scale;
+  pp.dq_out_mul = p.scale;
+  if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
   CUtensorMap tq, tk, tv, tdo;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BQ))) return rc;
   if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
@@ -371,7 +395,7 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
   attn_bwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, p);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
-  return simt::convert_dq_bf16(p, st);
+  return simt::convert_dq_bf16(pp, st);
 }
 
 }  // namespace tc
