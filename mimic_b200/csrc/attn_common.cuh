@@ -23,6 +23,7 @@ struct AttnParams {
   void *dq, *dk, *dv;
   float *dshift, *dw, *dbias;
   float *dq_acc, *delta_ws, *dz_ws;
+  int debug_flags = 0;
   float dq_seed_mul = 1.f, dq_out_mul = 1.f;   // dq_acc seed = dz*w*seed_mul; dq = dq_acc*out_mul
 };
 

@@ -19,6 +19,8 @@
 // TMEM map (512 cols): dV [0,128) dK [128,256) SdQ0 [256,320) SdQ1 [320,384) dP0 [384,448) dP1 [448,512).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "attn_common.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
@@ -37,15 +39,16 @@ constexpr int KV_TILE = 2 * KV_HALF;       // 32 KB
 constexpr int Q_HALF = BQ * 128;           // [64 rows][128 B] = 8 KB
 constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
 constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
-constexpr int STAGE_BYTES = BQ * HD * 4;   // fp32 dQ staging, 32 KB
+constexpr int STAGE_BYTES = 32 * HD * 4;   // fp32 dQ staging for 32 query rows, 16 KB (two bulk reduces per tile)
+constexpr int NQS = 3;                     // Q / dO TMA stages
 constexpr int THREADS = 448;                // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM quarter), warps 10-13 drain
 constexpr float LOG2E = 1.4426950408889634f;
 
-constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + 2 * Q_TILE, OFF_DS = OFF_DO + 2 * Q_TILE,
+constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + NQS * Q_TILE, OFF_DS = OFF_DO + NQS * Q_TILE,
               OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 2 * BQ * 16,
-              OFF_TMEM = OFF_BAR + 16 * 8, SMEM_BYTES = OFF_TMEM + 16 + 1024;
+              OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16 + 1024;
 
-enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, S_FULL = 5, SOFT_DONE = 7, DQ_FULL = 9, DRAIN_DONE = 11, DKV_FULL = 13, N_BARS = 14 };
+enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, N_BARS = 16 };
 
 constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_SDQ = 256, TM_DP = 384;
 constexpr uint32_t IDESC_ST = idesc_bf16(128, BQ, 0, 0);     // S^T, dP^T : A, B K-major
@@ -89,9 +92,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(&bars[KV_FULL], 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NQS; ++i) {
         mbar_init(&bars[QDO_FULL + i], 1);
         mbar_init(&bars[QDO_EMPTY + i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
         mbar_init(&bars[S_FULL + i], 1);
         mbar_init(&bars[SOFT_DONE + i], 256);
         mbar_init(&bars[DQ_FULL + i], 1);
@@ -121,10 +126,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tma_load_4d(sV, &tm_v, &bars[KV_FULL], 0, s0, kvh, b);
       tma_load_4d(sV + KV_HALF, &tm_v, &bars[KV_FULL], 64, s0, kvh, b);
       for (int i = 0; i < n; ++i) {
-        const int st = i & 1;
+        const int st = i % NQS;
         const int h = kvh * G + i / nq, qt = qt_first + i % nq;
         const bool nc = need_c(qt);
-        mbar_wait(&bars[QDO_EMPTY + st], ((i >> 1) & 1) ^ 1, 100 + st);
+        mbar_wait(&bars[QDO_EMPTY + st], ((i / NQS) & 1) ^ 1, 100 + st);
         mbar_expect_tx(&bars[QDO_FULL + st], nc ? 2 * Q_TILE : Q_TILE);
         tma_load_4d(sQ + st * Q_TILE, &tm_q, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
         tma_load_4d(sQ + st * Q_TILE + Q_HALF, &tm_q, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
@@ -141,23 +146,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                      ds_addr = smem_u32(sDS);
       mbar_wait(&bars[KV_FULL], 0, 200);
       auto issue_sdp = [&](int i) {
-        const int st = i & 1;
+        const int st = i & 1, qs = i % NQS;
         const int qt = qt_first + i % nq;
-        mbar_wait(&bars[QDO_FULL + st], (i >> 1) & 1, 210 + st);
+        mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
         mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
           mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + ko_kv, 16, 1024),
-                 smem_desc_sw128(q_addr + st * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
+                 smem_desc_sw128(q_addr + qs * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
         }
         if (need_c(qt)) {
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
             mma_ss(tmem_base + TM_DP + st * BQ, smem_desc_sw128(v_addr + ko_kv, 16, 1024),
-                   smem_desc_sw128(do_addr + st * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
+                   smem_desc_sw128(do_addr + qs * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
           }
         }
         tc_commit(&bars[S_FULL + st]);
@@ -165,7 +170,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       bool dv_started = false;
       issue_sdp(0);
       for (int i = 0; i < n; ++i) {
-        const int st = i & 1;
+        const int st = i & 1, qs = i % NQS;
         const int qt = qt_first + i % nq;
         if (i + 1 < n) issue_sdp(i + 1);
         mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
@@ -174,18 +179,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)       // dV += P^T dO_i : K = 16 queries per step (8 TMEM cols; 2 KB of dO rows)
             mma_ts(tmem_base + TM_DV, tmem_base + TM_SDQ + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
-                   smem_desc_sw128(do_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (dv_started || k > 0));
+                   smem_desc_sw128(do_addr + qs * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (dv_started || k > 0));
           dv_started = true;
         }
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k)         // dK += dS^T Q_i
           mma_ts(tmem_base + TM_DK, tmem_base + TM_DP + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
-                 smem_desc_sw128(q_addr + st * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (i > 0 || k > 0));
+                 smem_desc_sw128(q_addr + qs * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (i > 0 || k > 0));
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)         // dQ^T = K^T dS^T : K = 16 keys per step
           mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + k * 2048, KV_HALF, 1024),
                  smem_desc_sw128(ds_addr + st * DS_TILE + k * 2048, 16, 1024), IDESC_DQT, k > 0);
-        tc_commit(&bars[QDO_EMPTY + st]);
+        tc_commit(&bars[QDO_EMPTY + qs]);
         tc_commit(&bars[DQ_FULL + st]);
       }
       tc_commit(&bars[DKV_FULL]);
@@ -348,20 +353,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
-      if (did == 0) bulk_wait_read0();                  // previous bulk reduce finished reading the staging tile
-      named_bar_sync(2, 128);
+      const int rows = min(BQ, T - qt * BQ);
+      float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        stage[t * HD + c] = v0[t];
-        stage[(t + 32) * HD + c] = v1[t];
-      }
-      fence_proxy_async();
-      named_bar_sync(3, 128);
-      if (did == 0) {
-        const int rows = min(BQ, T - qt * BQ);
-        float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
-        bulk_reduce_add_f32(gdst, stage, (uint32_t)rows * HD * 4);
-        bulk_commit();
+      for (int half = 0; half < 2; ++half) {
+        if (did == 0) bulk_wait_read0();                // previous bulk reduce finished reading the staging tile
+        named_bar_sync(2, 128);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) stage[t * HD + c] = half ? v1[t] : v0[t];
+        fence_proxy_async();
+        named_bar_sync(3, 128);
+        if (did == 0 && !(p.debug_flags & 1)) {
+          const int r0 = half * 32, nr = min(32, rows - r0);
+          if (nr > 0) {
+            bulk_reduce_add_f32(gdst + (int64_t)r0 * HD, stage, (uint32_t)nr * HD * 4);
+            bulk_commit();
+          }
+        }
       }
     }
     if (did == 0) bulk_wait0();
@@ -381,6 +389,7 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   AttnParams pp = p;
   pp.dq_seed_mul = 1.f / p.scale;
   pp.dq_out_mul = p.scale;
+  if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pp.debug_flags = atoi(e);   // bit 0: skip the dQ reduce (timing experiments only)
   if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
   CUtensorMap tq, tk, tv, tdo;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BQ))) return rc;
