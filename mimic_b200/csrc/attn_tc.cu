@@ -135,22 +135,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && n > 0) {
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    // ===================== MMA issuer =====================
+    // All 32 lanes run the control flow (warp-uniform waits and address arithmetic); one elected lane issues.
+    if (n > 0) {
+      constexpr uint32_t HI = desc_hi_sw128(1024);
+      const uint32_t q_lo = desc_lo(smem_u32(sQ), 16), k_lo0 = desc_lo(smem_u32(sK), 16);
+      const uint32_t v_lo0 = desc_lo(smem_u32(sV), HALF_BYTES);          // V as MN-major B: d halves 16 KB apart
       mbar_wait(&bars[Q_FULL], 0, 200);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 210 + st);
         tc_fence_after();
+        if (elect_one()) {
+          const uint32_t k_lo = k_lo0 + st * (TILE_BYTES >> 4);
+          const uint32_t d_s = tmem_base + st * BN;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t koff = (k >> 2) * HALF_BYTES + (k & 3) * 32;
-          mma_ss(tmem_base + st * BN, smem_desc_sw128(q_addr + koff, 16, 1024),
-                 smem_desc_sw128(k_addr + st * TILE_BYTES + koff, 16, 1024), IDESC_QK, k > 0);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t koff = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
+            if (k == 0) mma_ss_c<false>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
+            else mma_ss_c<true>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
+          }
+          tc_commit(&bars[K_EMPTY + st]);
+          tc_commit(&bars[S_FULL + st]);
         }
-        tc_commit(&bars[K_EMPTY + st]);
-        tc_commit(&bars[S_FULL + st]);
+        __syncwarp();
       };
       issue_qk(0);
       if (n > 1) issue_qk(1);
@@ -161,19 +169,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (j <= jd) {
           mbar_wait(&bars[V_FULL + st], (j >> 1) & 1, 230 + st);
           tc_fence_after();
+          if (elect_one()) {
+            // A: P_j in TMEM, 16 bf16 of K per step = 8 columns; B: V_j [keys][d], 16 keys = 2048 B per step
+            const uint32_t v_lo = v_lo0 + st * (TILE_BYTES >> 4);
+            const uint32_t a_p = tmem_base + st * BN;
+            if (j > 0) {
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k) {
-            // A: P_j in TMEM, 16 bf16 of K per step = 8 columns; B: V_j [keys][d], 16 keys = 2048 B per step,
-            // 64-wide d halves 16 KB apart (LBO), 8-key groups 1 KB apart (SBO)
-            mma_ts(tmem_O, tmem_base + st * BN + k * 8,
-                   smem_desc_sw128(v_addr + st * TILE_BYTES + k * 2048, HALF_BYTES, 1024), IDESC_PV, (j > 0 || k > 0));
+              for (int k = 0; k < BN / 16; ++k) mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) {
+                if (k == 0) mma_ts_c<false>(tmem_O, a_p, desc64(HI, v_lo), IDESC_PV);
+                else mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+              }
+            }
+            tc_commit(&bars[V_EMPTY + st]);
+            tc_commit(&bars[PV_DONE]);
           }
-          tc_commit(&bars[V_EMPTY + st]);
-          tc_commit(&bars[PV_DONE]);
+          __syncwarp();
         }
         if (j + 2 < n) issue_qk(j + 2);
       }
-      tc_commit(&bars[O_FULL]);
+      if (elect_one()) tc_commit(&bars[O_FULL]);
+      __syncwarp();
     }
   } else {
     // ===================== softmax / correction / epilogue: one query row per thread =====================

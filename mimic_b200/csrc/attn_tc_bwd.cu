@@ -141,59 +141,96 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n > 0) {
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO),
-                     ds_addr = smem_u32(sDS);
+    // All 32 lanes run the control flow (waits, address arithmetic stay warp-uniform); one elected lane issues.
+    if (n > 0) {
+      constexpr uint32_t HI = desc_hi_sw128(1024);
+      const uint32_t k_km = desc_lo(smem_u32(sK), 16), v_km = desc_lo(smem_u32(sV), 16);        // K-major views
+      const uint32_t k_mn = desc_lo(smem_u32(sK), KV_HALF);                                      // K^T as MN-major A
+      const uint32_t q_km0 = desc_lo(smem_u32(sQ), 16), do_km0 = desc_lo(smem_u32(sDO), 16);
+      const uint32_t q_mn0 = desc_lo(smem_u32(sQ), Q_HALF), do_mn0 = desc_lo(smem_u32(sDO), Q_HALF);
+      const uint32_t ds_mn0 = desc_lo(smem_u32(sDS), 16);
       mbar_wait(&bars[KV_FULL], 0, 200);
       auto issue_sdp = [&](int i) {
         const int st = i & 1, qs = i % NQS;
         const int qt = qt_first + i % nq;
+        const bool nc = need_c(qt);
         mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
         mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
-          mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + ko_kv, 16, 1024),
-                 smem_desc_sw128(q_addr + qs * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
-        }
-        if (need_c(qt)) {
+        if (elect_one()) {
+          const uint32_t q_km = q_km0 + qs * (Q_TILE >> 4), do_km = do_km0 + qs * (Q_TILE >> 4);
+          const uint32_t d_s = tmem_base + TM_SDQ + st * BQ, d_p = tmem_base + TM_DP + st * BQ;
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
-            const uint32_t ko_kv = (k >> 2) * KV_HALF + (k & 3) * 32, ko_q = (k >> 2) * Q_HALF + (k & 3) * 32;
-            mma_ss(tmem_base + TM_DP + st * BQ, smem_desc_sw128(v_addr + ko_kv, 16, 1024),
-                   smem_desc_sw128(do_addr + qs * Q_TILE + ko_q, 16, 1024), IDESC_ST, k > 0);
+            const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+            if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
+            else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
           }
+          if (nc) {
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+              if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+              else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+            }
+          }
+          tc_commit(&bars[S_FULL + st]);
         }
-        tc_commit(&bars[S_FULL + st]);
+        __syncwarp();
       };
       bool dv_started = false;
       issue_sdp(0);
       for (int i = 0; i < n; ++i) {
         const int st = i & 1, qs = i % NQS;
         const int qt = qt_first + i % nq;
+        const bool nc = need_c(qt);
         if (i + 1 < n) issue_sdp(i + 1);
         mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
         tc_fence_after();
-        if (need_c(qt)) {
+        if (elect_one()) {
+          const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
+          const uint32_t ds_mn = ds_mn0 + st * (DS_TILE >> 4);
+          const uint32_t a_p = tmem_base + TM_SDQ + st * BQ, a_ds = tmem_base + TM_DP + st * BQ;
+          if (nc) {
+            // dV += P^T dO_i : K = 16 queries per step (8 packed TMEM cols: queries 0-31 at cols 0.., 32-63 at cols 48..)
+            if (dv_started) {
 #pragma unroll
-          for (int k = 0; k < BQ / 16; ++k)       // dV += P^T dO_i : K = 16 queries per step (8 TMEM cols; 2 KB of dO rows)
-            mma_ts(tmem_base + TM_DV, tmem_base + TM_SDQ + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
-                   smem_desc_sw128(do_addr + qs * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (dv_started || k > 0));
-          dv_started = true;
+              for (int k = 0; k < BQ / 16; ++k)
+                mma_ts_c<true>(tmem_base + TM_DV, a_p + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BQ / 16; ++k) {
+                if (k == 0) mma_ts_c<false>(tmem_base + TM_DV, a_p, desc64(HI, do_mn), IDESC_DKV);
+                else mma_ts_c<true>(tmem_base + TM_DV, a_p + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV);
+              }
+            }
+          }
+          // dK += dS^T Q_i
+          if (i > 0) {
+#pragma unroll
+            for (int k = 0; k < BQ / 16; ++k)
+              mma_ts_c<true>(tmem_base + TM_DK, a_ds + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BQ / 16; ++k) {
+              if (k == 0) mma_ts_c<false>(tmem_base + TM_DK, a_ds, desc64(HI, q_mn), IDESC_DKV);
+              else mma_ts_c<true>(tmem_base + TM_DK, a_ds + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV);
+            }
+          }
+          // dQ^T = K^T dS^T : K = 16 keys per step
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) {
+            if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
+            else mma_ss_c<true>(a_p, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
+          }
+          tc_commit(&bars[QDO_EMPTY + qs]);
+          tc_commit(&bars[DQ_FULL + st]);
         }
-#pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)         // dK += dS^T Q_i
-          mma_ts(tmem_base + TM_DK, tmem_base + TM_DP + st * BQ + (k < 2 ? k * 8 : 48 + (k - 2) * 8),
-                 smem_desc_sw128(q_addr + qs * Q_TILE + k * 2048, Q_HALF, 1024), IDESC_DKV, (i > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < BN / 16; ++k)         // dQ^T = K^T dS^T : K = 16 keys per step
-          mma_ss(tmem_base + TM_SDQ + st * BQ, smem_desc_sw128(k_addr + k * 2048, KV_HALF, 1024),
-                 smem_desc_sw128(ds_addr + st * DS_TILE + k * 2048, 16, 1024), IDESC_DQT, k > 0);
-        tc_commit(&bars[QDO_EMPTY + qs]);
-        tc_commit(&bars[DQ_FULL + st]);
+        __syncwarp();
+        if (nc) dv_started = true;
       }
-      tc_commit(&bars[DKV_FULL]);
+      if (elect_one()) tc_commit(&bars[DKV_FULL]);
+      __syncwarp();
     }
   } else if (warp < 10) {
     // ===================== softmax warps: one key row x 32 query columns per thread =====================
