@@ -31,24 +31,33 @@ constexpr int FWD_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.f;    // lazy O rescale: only when the running max grows by > 2^8
 
-enum FwdBar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, SOFT_DONE = 11, PV_DONE = 13, O_FULL = 14, N_FWD_BARS = 15 };
+// K / V rings have NKV stages each (3 when shared memory allows: the TMA round trip is longer than one tile of MMA work)
+enum FwdBar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 4, V_FULL = 7, V_EMPTY = 10, S_FULL = 13, SOFT_DONE = 15, PV_DONE = 17, O_FULL = 18, N_FWD_BARS = 19 };
 
 constexpr uint32_t IDESC_QK = idesc_bf16(BM, BN, 0, 0);   // A = Q (K-major), B = K (K-major)
 constexpr uint32_t IDESC_PV = idesc_bf16(BM, HD, 0, 1);   // A = P (TMEM),    B = V (MN-major: [keys][d])
 
 __device__ __forceinline__ uint32_t low_bits(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
+template <int NKV>
 struct FwdSmem {
-  static constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = 3 * TILE_BYTES, OFF_BAR = 5 * TILE_BYTES;
-  static constexpr int OFF_TMEM = OFF_BAR + 16 * 8, OFF_W = OFF_TMEM + 16, OFF_SHIFT = OFF_W + 512, OFF_KBITS = OFF_SHIFT + 512;
-  static size_t bytes(int S) { return 1024 + OFF_KBITS + (size_t)((S + BN - 1) / BN) * 4 * 4; }
+  static constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = (1 + NKV) * TILE_BYTES, OFF_BAR = (1 + 2 * NKV) * TILE_BYTES;
+  static constexpr int OFF_TMEM = OFF_BAR + 24 * 8, OFF_W = OFF_TMEM + 16, OFF_SHIFT = OFF_W + 512, OFF_KBITS = OFF_SHIFT + 512;
+  // the dynamic shared window starts 1024-byte aligned (no static __shared__ in this kernel; checked at entry)
+  static size_t bytes(int S) { return OFF_KBITS + (size_t)((S + BN - 1) / BN) * 4 * 4; }
 };
+constexpr size_t MAX_DYN_SMEM = 232448;
 
+template <int NKV>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using FwdSmem = FwdSmem<NKV>;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("[mimic tcgen05] dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem + FwdSmem::OFF_Q;
   uint8_t* sK = smem + FwdSmem::OFF_K;
   uint8_t* sV = smem + FwdSmem::OFF_V;
@@ -75,11 +84,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(&bars[Q_FULL], 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NKV; ++i) {
         mbar_init(&bars[K_FULL + i], 1);
         mbar_init(&bars[K_EMPTY + i], 1);
         mbar_init(&bars[V_FULL + i], 1);
         mbar_init(&bars[V_EMPTY + i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
         mbar_init(&bars[S_FULL + i], 1);
         mbar_init(&bars[SOFT_DONE + i], 128);
       }
@@ -120,8 +131,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, t0, h, b);
       tma_load_4d(sQ + HALF_BYTES, &tm_q, &bars[Q_FULL], 64, t0, h, b);
       for (int j = 0; j < n; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % NKV;
+        const uint32_t ph = (j / NKV) & 1;
         mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 100 + st);
         mbar_expect_tx(&bars[K_FULL + st], TILE_BYTES);
         tma_load_4d(sK + st * TILE_BYTES, &tm_k, &bars[K_FULL + st], 0, j * BN, kvh, b);
@@ -143,11 +154,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t v_lo0 = desc_lo(smem_u32(sV), HALF_BYTES);          // V as MN-major B: d halves 16 KB apart
       mbar_wait(&bars[Q_FULL], 0, 200);
       auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 210 + st);
+        const int st = j & 1, ks = j % NKV;
+        mbar_wait(&bars[K_FULL + ks], (j / NKV) & 1, 210 + ks);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t k_lo = k_lo0 + st * (TILE_BYTES >> 4);
+          const uint32_t k_lo = k_lo0 + ks * (TILE_BYTES >> 4);
           const uint32_t d_s = tmem_base + st * BN;
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
@@ -155,7 +166,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (k == 0) mma_ss_c<false>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
             else mma_ss_c<true>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
           }
-          tc_commit(&bars[K_EMPTY + st]);
+          tc_commit(&bars[K_EMPTY + ks]);
           tc_commit(&bars[S_FULL + st]);
         }
         __syncwarp();
@@ -167,11 +178,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(&bars[SOFT_DONE + st], (j >> 1) & 1, 220 + st);
         tc_fence_after();
         if (j <= jd) {
-          mbar_wait(&bars[V_FULL + st], (j >> 1) & 1, 230 + st);
+          const int vs = j % NKV;
+          mbar_wait(&bars[V_FULL + vs], (j / NKV) & 1, 230 + vs);
           tc_fence_after();
           if (elect_one()) {
             // A: P_j in TMEM, 16 bf16 of K per step = 8 columns; B: V_j [keys][d], 16 keys = 2048 B per step
-            const uint32_t v_lo = v_lo0 + st * (TILE_BYTES >> 4);
+            const uint32_t v_lo = v_lo0 + vs * (TILE_BYTES >> 4);
             const uint32_t a_p = tmem_base + st * BN;
             if (j > 0) {
 #pragma unroll
@@ -183,7 +195,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 else mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
               }
             }
-            tc_commit(&bars[V_EMPTY + st]);
+            tc_commit(&bars[V_EMPTY + vs]);
             tc_commit(&bars[PV_DONE]);
           }
           __syncwarp();
@@ -418,14 +430,22 @@ int fwd(const AttnParams& p, cudaStream_t st) {
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, 128))) return rc;
   if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, 128))) return rc;
   if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, 128))) return rc;
-  const size_t smem = FwdSmem::bytes(p.S);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   dim3 grid((p.T + BM - 1) / BM, p.H, p.B);
-  attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tk, tv, p);
+  const size_t smem3 = FwdSmem<3>::bytes(p.S), smem2 = FwdSmem<2>::bytes(p.S);
+  static size_t configured3 = 0, configured2 = 0;
+  if (smem3 <= MAX_DYN_SMEM) {
+    if (smem3 > configured3) {
+      MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      configured3 = smem3;
+    }
+    attn_fwd_tc_kernel<3><<<grid, FWD_THREADS, smem3, st>>>(tq, tk, tv, p);
+  } else {
+    if (smem2 > configured2) {
+      MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = smem2;
+    }
+    attn_fwd_tc_kernel<2><<<grid, FWD_THREADS, smem2, st>>>(tq, tk, tv, p);
+  }
   MIMIC_LAUNCH_OK("attn_fwd_tc_kernel");
   return MIMIC_OK;
 }

@@ -155,7 +155,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int qt = qt_first + i % nq;
         const bool nc = need_c(qt);
         mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
-        mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
+        if (!(p.debug_flags & 2)) mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
         tc_fence_after();
         if (elect_one()) {
           const uint32_t q_km = q_km0 + qs * (Q_TILE >> 4), do_km = do_km0 + qs * (Q_TILE >> 4);
@@ -288,7 +288,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       uint32_t pk[16], dk_[16];
       const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFFFFFu);
       const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFFFFFu);
-      if (all_v && nc) {
+      if (p.debug_flags & 4) {
+#pragma unroll
+        for (int c2 = 0; c2 < 16; ++c2) { pk[c2] = __float_as_uint(sv[c2]); dk_[c2] = __float_as_uint(sv[c2 + 16]); }
+      } else if (all_v && nc) {
         // interior causal tile: every entry visible.  dS (unscaled) = P (dP - Delta'); scale is applied to dK / dQ later
 #pragma unroll
         for (int c2 = 0; c2 < 16; ++c2) {
