@@ -15,6 +15,8 @@
 // TMEM map (512 cols): S0 [0,128) S1 [128,256) O [256,384); P_j = first 64 cols of S[j&1].
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "attn_common.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
@@ -424,7 +426,11 @@ bool supports(const AttnParams& p, bool backward) {
   return p.dtype == MIMIC_BF16 && p.d == HD && p.S <= (1 << 18) && p.T >= 1;
 }
 
+int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query tiles per CTA
+
 int fwd(const AttnParams& p, cudaStream_t st) {
+  // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
+  if (p.T > BM && getenv("MIMIC_FWD_V1") == nullptr) return fwd2(p, st);
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, 128))) return rc;

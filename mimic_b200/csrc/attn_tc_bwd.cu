@@ -129,7 +129,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int st = i % NQS;
         const int h = kvh * G + i / nq, qt = qt_first + i % nq;
         const bool nc = need_c(qt);
-        mbar_wait(&bars[QDO_EMPTY + st], ((i / NQS) & 1) ^ 1, 100 + st);
+        if (!(p.debug_flags & 8)) mbar_wait(&bars[QDO_EMPTY + st], ((i / NQS) & 1) ^ 1, 100 + st);
         mbar_expect_tx(&bars[QDO_FULL + st], nc ? 2 * Q_TILE : Q_TILE);
         tma_load_4d(sQ + st * Q_TILE, &tm_q, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
         tma_load_4d(sQ + st * Q_TILE + Q_HALF, &tm_q, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
@@ -154,19 +154,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int st = i & 1, qs = i % NQS;
         const int qt = qt_first + i % nq;
         const bool nc = need_c(qt);
-        mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
+        if (!(p.debug_flags & 16)) mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
         if (!(p.debug_flags & 2)) mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
         tc_fence_after();
         if (elect_one()) {
           const uint32_t q_km = q_km0 + qs * (Q_TILE >> 4), do_km = do_km0 + qs * (Q_TILE >> 4);
           const uint32_t d_s = tmem_base + TM_SDQ + st * BQ, d_p = tmem_base + TM_DP + st * BQ;
+          if (!(p.debug_flags & 128))
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
             if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
             else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
           }
-          if (nc) {
+          if (nc && !(p.debug_flags & 128)) {
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {
               const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
@@ -191,7 +192,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
           const uint32_t ds_mn = ds_mn0 + st * (DS_TILE >> 4);
           const uint32_t a_p = tmem_base + TM_SDQ + st * BQ, a_ds = tmem_base + TM_DP + st * BQ;
-          if (nc) {
+          if (nc && !(p.debug_flags & 64)) {
             // dV += P^T dO_i : K = 16 queries per step (8 packed TMEM cols: queries 0-31 at cols 0.., 32-63 at cols 48..)
             if (dv_started) {
 #pragma unroll
@@ -206,7 +207,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
           }
           // dK += dS^T Q_i
-          if (i > 0) {
+          if (p.debug_flags & 64) {
+          } else if (i > 0) {
 #pragma unroll
             for (int k = 0; k < BQ / 16; ++k)
               mma_ts_c<true>(tmem_base + TM_DK, a_ds + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV);
@@ -218,6 +220,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
           }
           // dQ^T = K^T dS^T : K = 16 keys per step
+          if (!(p.debug_flags & 32))
 #pragma unroll
           for (int k = 0; k < BN / 16; ++k) {
             if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
@@ -269,7 +272,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int t0 = qt * BQ;
       const bool nc = need_c(qt);
       if (i + 1 < n && sid < BQ) load_stats(i + 1, nxt);        // prefetch next iteration's row statistics
-      named_bar_sync(1, 256);                                   // stats[st] complete; stats[st^1] no longer read
+      if (!(p.debug_flags & 2048)) named_bar_sync(1, 256);      // stats[st] complete; stats[st^1] no longer read
       mbar_wait(&bars[S_FULL + st], (i >> 1) & 1, 310 + st);
       tc_fence_after();
       const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ;
@@ -333,6 +336,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (nc) tmem_st16(t_s + pcol, pk);                        // P^T  (A operand of dV)
       tmem_st16(t_dp + pcol, dk_);                              // dS^T (A operand of dK)
       // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
+      if (!(p.debug_flags & 512))
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int chunk = hf * 4 + ch;
@@ -341,7 +345,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       if (i + 1 < n && sid < BQ) stats[(st ^ 1) * BQ + sid] = nxt;
       tc_wait_st();
-      fence_proxy_async();                                      // smem dS^T visible to the tensor-core (async) proxy
+      if (!(p.debug_flags & 1024)) fence_proxy_async();         // smem dS^T visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
     }
@@ -393,6 +397,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
+      if (p.debug_flags & 256) continue;
       const int rows = min(BQ, T - qt * BQ);
       float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
 #pragma unroll
@@ -442,7 +447,7 @@ int bwd(const AttnParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
-  attn_bwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, p);
+  attn_bwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
   return simt::convert_dq_bf16(pp, st);
 }
