@@ -162,11 +162,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (elect_one()) {
           const uint32_t k_lo = k_lo0 + ks * (TILE_BYTES >> 4);
           const uint32_t d_s = tmem_base + st * BN;
+          for (int rep = 0; rep <= p.debug_flags; ++rep) {   // debug_flags > 0: re-issue QK^T (timing experiments)
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t koff = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
             if (k == 0) mma_ss_c<false>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
             else mma_ss_c<true>(d_s, desc64(HI, q_lo + koff), desc64(HI, k_lo + koff), IDESC_QK);
+          }
           }
           tc_commit(&bars[K_EMPTY + ks]);
           tc_commit(&bars[S_FULL + st]);
@@ -431,6 +433,8 @@ int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query 
 int fwd(const AttnParams& p, cudaStream_t st) {
   // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
   if (p.T > BM && getenv("MIMIC_FWD_V1") == nullptr) return fwd2(p, st);
+  AttnParams pd = p;
+  if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pd.debug_flags = atoi(e);
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, 128))) return rc;
@@ -444,13 +448,13 @@ int fwd(const AttnParams& p, cudaStream_t st) {
       MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
       configured3 = smem3;
     }
-    attn_fwd_tc_kernel<3><<<grid, FWD_THREADS, smem3, st>>>(tq, tk, tv, p);
+    attn_fwd_tc_kernel<3><<<grid, FWD_THREADS, smem3, st>>>(tq, tk, tv, pd);
   } else {
     if (smem2 > configured2) {
       MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       configured2 = smem2;
     }
-    attn_fwd_tc_kernel<2><<<grid, FWD_THREADS, smem2, st>>>(tq, tk, tv, p);
+    attn_fwd_tc_kernel<2><<<grid, FWD_THREADS, smem2, st>>>(tq, tk, tv, pd);
   }
   MIMIC_LAUNCH_OK("attn_fwd_tc_kernel");
   return MIMIC_OK;
