@@ -119,7 +119,8 @@ MIMIC_API int mimic_record_gather(const void* src, int64_t src_row_stride, int32
  *   dh_ptrs  device array of L pointers to [rows, D] contiguous gradients in h dtype, fully
  *            written (zeros on unselected rows): dH = grad_scale * 2 * row_w * (H - H').
  *            NULL = forward only.
- *   loss     fp32 [1], overwritten.   partial: fp32 workspace of mimic_mse_workspace() bytes.
+ *   loss     fp32 [1], overwritten.   workspace: mimic_mse_workspace() bytes, ZERO on first use (the kernel
+ *            keeps an arrival counter there and leaves it zero): one launch, deterministic final sum.
  * ------------------------------------------------------------------------------------------ */
 MIMIC_API size_t mimic_mse_workspace(int32_t L, int32_t rows, int32_t D);
 MIMIC_API int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype,
@@ -137,22 +138,25 @@ MIMIC_API int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride,
  *   dlogits [R, V] contiguous-or-same-stride as logits (may alias logits); NULL = forward only:
  *            dlogits = grad_scale * (softmax(logits) - onehot(label)) / n_kept, 0 on ignored rows.
  *   loss fp32 [1] overwritten with the mean over kept rows (0 when none); n_kept int32 [1].
+ *   workspace: mimic_ce_workspace(R) bytes, ZERO on first use (arrival counter + per-row losses).
  * ------------------------------------------------------------------------------------------ */
+MIMIC_API size_t mimic_ce_workspace(int32_t R);
 MIMIC_API int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, int32_t dtype,
                      const int64_t* labels, void* dlogits, float grad_scale,
-                     int32_t R, int32_t V, float* loss, int32_t* n_kept, void* stream);
+                     int32_t R, int32_t V, float* loss, int32_t* n_kept,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * On-device optimizer step for the flat fp32 shift-parameter buffer: global-norm clip
  * (train.yaml grad_clip_val) + AdamW with per-element weight decay (the reference's two groups,
  * src/shift_model.py:306-372: names containing "bias" get 0).  Replaces DeepSpeedCPUAdam's host
- * round trip.  lr arrives as a device scalar so a captured graph can replay it.
+ * round trip.  What changes per step arrives in device memory so a captured CUDA graph can replay it:
+ *   hyper: fp32 [3] = { lr, 1 - beta1^step, sqrt(1 - beta2^step) }.
  *   sumsq: fp32 [1] workspace.  grad is scaled in place by grad_mul (1/world, 1/accum) first.
  * ------------------------------------------------------------------------------------------ */
 MIMIC_API int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
-                     const float* weight_decay, int64_t n, const float* lr, float beta1, float beta2,
-                     float eps, int32_t step, float grad_mul, float max_norm, float* sumsq,
-                     void* stream);
+                     const float* weight_decay, int64_t n, const float* hyper, float beta1, float beta2,
+                     float eps, float grad_mul, float max_norm, float* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const void* const* __r
                                                           const int32_t* __restrict__ row_to_compact,
                                                           const float* __restrict__ row_w,
                                                           void* const* __restrict__ dh_ptrs, float grad_scale, int L,
-                                                          int rows, int N, int D, float* __restrict__ partial) {
+                                                          int rows, int N, int D, float* __restrict__ partial,
+                                                          unsigned int* __restrict__ counter, float* __restrict__ loss) {
   __shared__ float red[32];
+  __shared__ bool is_last;
   const int chunks = D / 8;
   const int64_t items = (int64_t)L * rows;
   float acc = 0.f;
@@ -131,20 +133,28 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const void* const* __r
     }
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
-
-__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
-  __shared__ float red[32];
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) out[0] = acc;
+  // the last CTA to finish sums the per-CTA partials in a fixed order (deterministic) and re-arms the counter
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      loss[0] = tot;
+      *counter = 0u;
+    }
+  }
 }
 
 static int mse_grid(int L, int rows) {
   const int64_t items = (int64_t)L * rows;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * 4;      // 64 registers x 256 threads: 4 resident CTAs per SM, one wave
   return (int)(items < cap ? items : cap);
 }
 
@@ -170,25 +180,24 @@ __device__ __forceinline__ void online_add(float& m, float& s, float x) {
   }
 }
 
-__global__ void ce_count_kernel(const int64_t* __restrict__ labels, int R, int32_t* __restrict__ n_kept, float* __restrict__ loss) {
-  __shared__ float red[32];
-  float c = 0.f;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) c += labels[i] >= 0 ? 1.f : 0.f;
-  c = block_sum(c, red);
-  if (threadIdx.x == 0) {
-    n_kept[0] = (int32_t)(c + 0.5f);
-    loss[0] = 0.f;
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ logits, int64_t row_stride,
                                                          const int64_t* __restrict__ labels, T* dlogits,
-                                                         float grad_scale, int R, int V,
-                                                         const int32_t* __restrict__ n_kept, float* __restrict__ loss) {
+                                                         float grad_scale, int R, int V, int32_t* __restrict__ n_kept,
+                                                         float* __restrict__ loss, float* __restrict__ row_loss,
+                                                         unsigned int* __restrict__ counter) {
   __shared__ float red[32];
   __shared__ float bc[2];
-  const float inv_n = n_kept[0] > 0 ? 1.f / (float)n_kept[0] : 0.f;
+  __shared__ bool is_last;
+  // every CTA counts the kept rows itself (R labels: a few KB from L2) — no separate counting launch
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += labels[i] >= 0 ? 1.f : 0.f;
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) bc[0] = cnt;
+  __syncthreads();
+  const float n_keep = bc[0];
+  __syncthreads();
+  const float inv_n = n_keep > 0.f ? 1.f / n_keep : 0.f;
   for (int r = blockIdx.x; r < R; r += gridDim.x) {
     const T* x = logits + (int64_t)r * row_stride;
     T* dx = dlogits ? dlogits + (int64_t)r * row_stride : nullptr;
@@ -197,6 +206,7 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
     const int body = (V - head) / 8;
     const int tail0 = head + body * 8;
     if (label < 0) {
+      if (threadIdx.x == 0) row_loss[r] = 0.f;
       if (dx) {
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int i = threadIdx.x; i < head; i += blockDim.x) dx[i] = from_f32<T>(0.f);
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
     gm = bc[0];
     const float lse = gm + __logf(bc[1]);
     const float inv_sum = 1.f / bc[1];
-    if (threadIdx.x == 0) atomicAdd(loss, (lse - to_f32(x[label])) * inv_n);
+    if (threadIdx.x == 0) row_loss[r] = lse - to_f32(x[label]);
     if (dx) {
       const float gs = grad_scale * inv_n;
       // pass 2: gradient.  x may alias dx: every element is read before it is written by the
@@ -265,6 +275,23 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
     }
     __syncthreads();
   }
+  // last CTA: deterministic sum of the row losses, mean over kept rows
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      loss[0] = tot * inv_n;
+      n_kept[0] = (int32_t)(n_keep + 0.5f);
+      *counter = 0u;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -283,9 +310,9 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ gra
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                                                     float* __restrict__ v, const float* __restrict__ wd, int64_t n,
-                                                    const float* __restrict__ lr_p, float beta1, float beta2, float eps,
-                                                    float bc1, float bc2_sqrt, float max_norm, const float* __restrict__ sumsq) {
-  const float lr = lr_p[0];
+                                                    const float* __restrict__ hyper, float beta1, float beta2, float eps,
+                                                    float max_norm, const float* __restrict__ sumsq) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
   float clip = 1.f;
   if (max_norm > 0.f) {
     const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);   // torch.nn.utils.clip_grad_norm_
@@ -333,7 +360,7 @@ extern "C" int mimic_record_gather(const void* src, int64_t src_row_stride, int3
 
 extern "C" size_t mimic_mse_workspace(int32_t L, int32_t rows, int32_t D) {
   (void)D;
-  return (size_t)(mse_grid(L, rows) + 1) * sizeof(float);
+  return (size_t)(mse_grid(L, rows) + 4) * sizeof(float);   // per-CTA partials + the arrival counter
 }
 
 extern "C" int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype, const void* hp,
@@ -346,38 +373,43 @@ extern "C" int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride
   MIMIC_CHECK_ARG(workspace_bytes >= mimic_mse_workspace(L, rows, D), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = mse_grid(L, rows);
-  float* partial = static_cast<float*>(workspace);
+  float* partial = static_cast<float*>(workspace) + 4;
+  unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
   if (h_dtype == MIMIC_BF16)
-    mse_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
-                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial);
+    mse_fwd_bwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
   else if (h_dtype == MIMIC_F32)
     mse_fwd_bwd_kernel<float, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w,
-                                                       dh_ptrs, grad_scale, L, rows, N, D, partial);
+                                                       dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
   else {
     set_error("mse: unsupported dtype %d", h_dtype);
     return MIMIC_ERR_UNSUPPORTED;
   }
   MIMIC_LAUNCH_OK("mse_fwd_bwd_kernel");
-  sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, loss);
-  MIMIC_LAUNCH_OK("sum_partials_kernel");
   return MIMIC_OK;
 }
 
+extern "C" size_t mimic_ce_workspace(int32_t R) { return (size_t)(R + 4) * sizeof(float); }
+
 extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, int32_t dtype, const int64_t* labels,
                                 void* dlogits, float grad_scale, int32_t R, int32_t V, float* loss, int32_t* n_kept,
-                                void* stream) {
-  MIMIC_CHECK_ARG(logits && labels && loss && n_kept, "NULL argument");
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  MIMIC_CHECK_ARG(logits && labels && loss && n_kept && workspace, "NULL argument");
   MIMIC_CHECK_ARG(R > 0 && V > 0 && logits_row_stride >= V, "bad shape");
+  MIMIC_CHECK_ARG(workspace_bytes >= mimic_ce_workspace(R), "workspace too small");
+  if (dlogits)
+    MIMIC_CHECK_ARG((reinterpret_cast<uintptr_t>(dlogits) & 31u) == (reinterpret_cast<uintptr_t>(logits) & 31u),
+                    "logits and dlogits must share their alignment modulo 32 bytes");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  ce_count_kernel<<<1, 256, 0, st>>>(labels, R, n_kept, loss);
-  MIMIC_LAUNCH_OK("ce_count_kernel");
+  unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
+  float* row_loss = static_cast<float*>(workspace) + 4;
   const int grid = R < num_sms() * 4 ? R : num_sms() * 4;
   if (dtype == MIMIC_BF16)
     ce_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)logits, logits_row_stride, labels,
-                                                           (__nv_bfloat16*)dlogits, grad_scale, R, V, n_kept, loss);
+                                                           (__nv_bfloat16*)dlogits, grad_scale, R, V, n_kept, loss, row_loss, counter);
   else if (dtype == MIMIC_F32)
     ce_fwd_bwd_kernel<float><<<grid, 512, 0, st>>>((const float*)logits, logits_row_stride, labels, (float*)dlogits,
-                                                   grad_scale, R, V, n_kept, loss);
+                                                   grad_scale, R, V, n_kept, loss, row_loss, counter);
   else {
     set_error("ce: unsupported dtype %d", dtype);
     return MIMIC_ERR_UNSUPPORTED;
@@ -387,19 +419,16 @@ extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, i
 }
 
 extern "C" int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* weight_decay,
-                                int64_t n, const float* lr, float beta1, float beta2, float eps, int32_t step,
-                                float grad_mul, float max_norm, float* sumsq, void* stream) {
-  MIMIC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && weight_decay && lr && sumsq, "NULL argument");
-  MIMIC_CHECK_ARG(n > 0 && step >= 1, "bad n/step");
+                                int64_t n, const float* hyper, float beta1, float beta2, float eps, float grad_mul,
+                                float max_norm, float* sumsq, void* stream) {
+  MIMIC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && weight_decay && hyper && sumsq, "NULL argument");
+  MIMIC_CHECK_ARG(n > 0, "bad n");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MIMIC_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(float), st));
   const int grid = (int)((n + 255) / 256 < (int64_t)num_sms() * 4 ? (n + 255) / 256 : (int64_t)num_sms() * 4);
   grad_sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_mul, sumsq);
   MIMIC_LAUNCH_OK("grad_sumsq_kernel");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, weight_decay, n, lr, beta1, beta2, eps, bc1,
-                                     bc2_sqrt, max_norm, sumsq);
+  adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, weight_decay, n, hyper, beta1, beta2, eps, max_norm, sumsq);
   MIMIC_LAUNCH_OK("adamw_kernel");
   return MIMIC_OK;
 }

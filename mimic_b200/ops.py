@@ -58,6 +58,21 @@ class KernelTimer:
 timer = KernelTimer()
 
 
+_zero_ws_cache = {}
+graph_keepalive = []          # pinned host staging captured by CUDA graphs must outlive the autograd graph
+
+
+def _zero_ws(dev, nbytes: int, tag: str) -> torch.Tensor:
+    """Persistent zero-initialised workspace (the single-launch loss kernels keep a self-resetting arrival
+    counter in it).  One per (device, kernel); grown on demand."""
+    key = (dev, tag)
+    ws = _zero_ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=dev)
+        _zero_ws_cache[key] = ws
+    return ws
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -229,21 +244,25 @@ class _AlignMSE(torch.autograd.Function):
         if need_grad:
             step = rows * D * dh.element_size()
             ptrs += [dh.data_ptr() + l * step for l in range(L)]
-        ptr_t = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=True)
+        ptr_host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+        ptr_t = torch.empty(len(ptrs), dtype=torch.int64, device=dev)
+        ptr_t.copy_(ptr_host, non_blocking=True)
+        if torch.cuda.is_current_stream_capturing():
+            graph_keepalive.append(ptr_host)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         nbytes = lib.mimic_mse_workspace(L, rows, D)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _zero_ws(dev, nbytes, "mse")
         _ev = timer.start("mse_fwd_bwd")
         check(lib.mimic_mse_fwd_bwd(ptr_t.data_ptr(), D, _DT[h0.dtype], _ptr(hp), _DT[hp.dtype], _ptr(row_to_compact),
                                     _ptr(row_w), (ptr_t.data_ptr() + 8 * L) if need_grad else None, float(grad_scale),
                                     L, rows, N, D, _ptr(loss), _ptr(ws), nbytes, _stream()), "mimic_mse_fwd_bwd")
         timer.stop(_ev)
-        _count(2)
+        _count(1)
         ctx.dh = dh
         ctx.shapes = [h.shape for h in hs]
         ctx.grad_scale = grad_scale
         ctx.assume_folded = assume_folded
-        ctx.keepalive = (ptr_t, hs)
+        ctx.keepalive = (ptr_t, ptr_host, hs)
         return loss[0]
 
     @staticmethod
@@ -281,11 +300,13 @@ class _CELoss(torch.autograd.Function):
             dlog = lg if inplace else torch.empty_like(lg)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         n_kept = torch.empty(1, dtype=torch.int32, device=dev)
+        nbytes = lib.mimic_ce_workspace(R)
+        ws = _zero_ws(dev, nbytes, "ce")
         _ev = timer.start("ce_fwd_bwd")
         check(lib.mimic_ce_fwd_bwd(_ptr(lg), lg.stride(0), _DT[lg.dtype], _ptr(labels), _ptr(dlog), float(grad_scale),
-                                   R, V, _ptr(loss), _ptr(n_kept), _stream()), "mimic_ce_fwd_bwd")
+                                   R, V, _ptr(loss), _ptr(n_kept), _ptr(ws), nbytes, _stream()), "mimic_ce_fwd_bwd")
         timer.stop(_ev)
-        _count(2)
+        _count(1)
         ctx.dlog = dlog
         ctx.shape = logits.shape
         ctx.grad_scale = grad_scale
@@ -310,13 +331,19 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0,
     return _CELoss.apply(logits, labels, grad_scale, assume_folded, inplace)
 
 
-def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, lr: torch.Tensor, step: int, *, betas=(0.9, 0.999),
+def adamw_hyper(lr: float, step: int, betas=(0.9, 0.999)) -> torch.Tensor:
+    """Host-side [lr, 1-beta1^step, sqrt(1-beta2^step)] (pinned) — copy it into the device `hyper` tensor."""
+    return torch.tensor([lr, 1.0 - betas[0] ** step, math.sqrt(1.0 - betas[1] ** step)], dtype=torch.float32)
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper: torch.Tensor, *, betas=(0.9, 0.999),
                eps=1e-8, grad_mul=1.0, max_norm=0.0, sumsq: Optional[torch.Tensor] = None) -> None:
-    """Clip (global norm) + AdamW on flat fp32 buffers, on device (replaces DeepSpeedCPUAdam)."""
-    _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, lr)
+    """Clip (global norm) + AdamW on flat fp32 buffers, on device (replaces DeepSpeedCPUAdam).
+    hyper: device fp32 [3] = adamw_hyper(lr, step) (device-resident so a CUDA graph can replay the step)."""
+    _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper)
     if sumsq is None:
         sumsq = torch.empty(1, dtype=torch.float32, device=param.device)
     check(lib.mimic_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(weight_decay),
-                               param.numel(), _ptr(lr), betas[0], betas[1], eps, int(step), float(grad_mul),
+                               param.numel(), _ptr(hyper), betas[0], betas[1], eps, float(grad_mul),
                                float(max_norm), _ptr(sumsq), _stream()), "mimic_adamw_step")
     _count(2)

@@ -80,12 +80,21 @@ class MimicTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         dev = self.flat.param.device
-        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)       # lr, bias corrections (device: graph replay)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.opt_step = 0
         self.micro = 0
+        self._graph = None
+        self._static = None
+        # Every step (eager warm-up, capture, replay) runs on this one non-default stream: autograd binds each
+        # leaf's gradient accumulator to the stream of its first use, and a capture only accepts same-stream edges.
+        self.stream = torch.cuda.Stream(device=dev)
 
     def micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
+        with torch.cuda.stream(self.stream):
+            return self._micro_step(inputs, query_inputs)
+
+    def _micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
         """One micro-batch: forward (2 passes) + backward.  Steps the optimizer every `accum` calls."""
         if self.micro % self.accum == 0:
             self.flat.grad_and_scalars.zero_()
@@ -99,19 +108,83 @@ class MimicTrainer:
             self.optimizer_step()
         return loss_dict
 
-    def optimizer_step(self) -> None:
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad_and_scalars, group=self.pg)      # the only collective of the path
+    def _advance_schedule(self) -> None:
+        """Host side of an optimizer step: step counter, cosine-with-warm-up lr, Adam bias corrections ->
+        device `hyper` (12 bytes; enqueued before the kernels / graph that read it)."""
         self.opt_step += 1
         lr = self.base_lr * cosine_with_warmup(self.opt_step - 1, self.warmup, self.total_steps)
-        self.lr_dev.fill_(lr)
+        # pageable source: the driver stages the 12 bytes at call time, so the host may run many replays ahead
+        # without racing on a shared pinned buffer
+        self.hyper.copy_(ops.adamw_hyper(lr, self.opt_step))
+
+    def _device_optimizer_step(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad_and_scalars, group=self.pg)      # the only collective of the path
         ops.adamw_step(self.flat.param, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq,
-                       self.flat.weight_decay, self.lr_dev, self.opt_step, grad_mul=1.0 / self.world,
+                       self.flat.weight_decay, self.hyper, grad_mul=1.0 / self.world,
                        max_norm=self.clip, sumsq=self.sumsq)
+
+    def optimizer_step(self) -> None:
+        self._advance_schedule()
+        self._device_optimizer_step()
+
+    # ---- whole-step CUDA graph -----------------------------------------------------------------------
+    def capture(self, inputs: Optional[dict], query_inputs: dict) -> None:
+        """Capture one full optimizer step (accum micro-batches of: context pass, shifted query pass, losses,
+        backward; then all-reduce, clip, AdamW) into a CUDA graph over static input buffers.  The eager step is
+        launch-bound on a busy host (~4000 small launches); replay removes the host from the loop.  Call after
+        a few eager steps (allocations, hook installation and the forward replacement must have happened)."""
+        assert self.micro % self.accum == 0, "capture at an optimizer-step boundary"
+        with torch.cuda.stream(self.stream):
+            self._capture(inputs, query_inputs)
+
+    def _capture(self, inputs, query_inputs) -> None:
+        self._static = ([{k: v.clone() for k, v in (inputs or {}).items()} for _ in range(self.accum)],
+                        [{k: v.clone() for k, v in query_inputs.items()} for _ in range(self.accum)])
+        # warm-up and capture run real optimizer kernels: neutralise them (lr 0) and restore the state after
+        snap = [t.clone() for t in (self.flat.param, self.flat.exp_avg, self.flat.exp_avg_sq, self.hyper)]
+        self.hyper.copy_(torch.tensor([0.0, 1.0, 1.0], device=self.hyper.device))
+        self._graph_body()                                  # one more warm-up, same stream
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=self.stream):
+            self._graph_body()
+        torch.cuda.synchronize()
+        for dst, src in zip((self.flat.param, self.flat.exp_avg, self.flat.exp_avg_sq, self.hyper), snap):
+            dst.copy_(src)
+
+    def _graph_body(self) -> None:
+        self.flat.grad_and_scalars.zero_()
+        for a in range(self.accum):
+            ins, qs = self._static[0][a], self._static[1][a]
+            loss_dict = self.sm.forward_inputs(ins if ins else None, qs, fold_scale=1.0 / self.accum)
+            (loss_dict["loss"] / self.accum).backward()
+            for i, key in enumerate(("loss", "ce_loss", "ffn_mse_loss")):
+                if key in loss_dict:
+                    self.flat.scalars[i] += loss_dict[key].detach().float() / self.accum
+        self._device_optimizer_step()
+
+    def graph_step(self, batches) -> None:
+        """Replay the captured step on `accum` new micro-batches [(inputs, query_inputs), ...] of the captured
+        shapes (host or device tensors; copied into the static buffers)."""
+        assert self._graph is not None, "call capture() first"
+        with torch.cuda.stream(self.stream):
+            self._graph_step(batches)
+
+    def _graph_step(self, batches) -> None:
+        for a, (ins, qs) in enumerate(batches):
+            for k, v in (ins or {}).items():
+                self._static[0][a][k].copy_(v, non_blocking=True)
+            for k, v in qs.items():
+                self._static[1][a][k].copy_(v, non_blocking=True)
+        self._advance_schedule()
+        self._graph.replay()
+        self.micro += self.accum
 
     def logged_scalars(self) -> Dict[str, float]:
         """Mean over ranks of the loss terms of the last optimizer step (one D2H read)."""
-        vals = (self.flat.scalars / self.world).tolist()
+        with torch.cuda.stream(self.stream):
+            vals = (self.flat.scalars / self.world).tolist()
         return dict(zip(("loss", "ce_loss", "ffn_mse_loss"), vals))
 
     # encoder.pth, same keys as the reference's save_pretrained (src/utils.py:96-102)

@@ -146,13 +146,12 @@ def test_adamw_step_matches_torch():
     opt = torch.optim.AdamW([{"params": [pa], "weight_decay": 0.0}, {"params": [pb], "weight_decay": 1e-3}], lr=5e-3)
     p = p0.clone().cuda()
     m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
-    lr = torch.tensor([5e-3], device="cuda")
     for step in range(1, 4):
         g = torch.randn(n) * 3
         pa.grad, pb.grad = g[wd == 0].clone(), g[wd != 0].clone()
         torch.nn.utils.clip_grad_norm_([pa, pb], 1.0)
         opt.step()
-        ops.adamw_step(p, g.cuda(), m, v, wd.cuda(), lr, step, max_norm=1.0)
+        ops.adamw_step(p, g.cuda(), m, v, wd.cuda(), ops.adamw_hyper(5e-3, step).cuda(), max_norm=1.0)
         want = torch.empty(n)
         want[wd == 0], want[wd != 0] = pa.detach(), pb.detach()
         assert rel(p, want) < 1e-6

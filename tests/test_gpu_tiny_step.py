@@ -44,8 +44,8 @@ def test_tiny_step_matches_reference():
     params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
     grads = torch.autograd.grad(loss_dict["loss"], list(params.values()))
     # first step: the context pass still runs the stock HF attention (forward is replaced at
-    # register_shift_hooks, src/shift_encoder.py:639-645): 4 gathers + 4 fused fwd + mse(2) + ce(2) + 4 bwd(3)
-    assert ops.launch_count - n0 >= 4 + 4 + 2 + 2 + 4 * 3
+    # register_shift_hooks, src/shift_encoder.py:639-645): 4 gathers + 4 fused fwd + mse + ce + 4 bwd(3)
+    assert ops.launch_count - n0 >= 4 + 4 + 1 + 1 + 4 * 3
     for (n, p), g in zip(params.items(), grads):
         assert rel(g, z["grad." + n]) < 2e-4, n
     # handles are inactive again, hooks removed (src/shift_model.py:262)

@@ -61,3 +61,28 @@ def test_training_reduces_loss(dtype):
     assert set(sc) == {"loss", "ce_loss", "ffn_mse_loss"} and sc["loss"] > 0
     ck = tr.state_dict_for_checkpoint()
     assert set(ck) == {"attn_shift"} | {f"log_Z1_lin.{l}.{k}" for l in range(4) for k in ("weight", "bias")}
+
+
+def test_graph_replay_equals_eager():
+    """The whole-step CUDA graph (trainer.capture / graph_step) trains exactly like the eager step."""
+    from mimic_b200.trainer import MimicTrainer
+    finals = []
+    for mode in ("eager", "graph"):
+        sm, enc, full, qa = _setup(torch.float32, seed=7)
+        tr = MimicTrainer(sm, lr=5e-3, warmup_step=2, total_steps=50, accumulate_grad_batches=1)
+        batches = [(full.roll(i, 1), qa) for i in range(6)]
+        for i in range(2):                                   # hooks installed, forward replaced, buffers allocated
+            tr.micro_step({"input_ids": batches[i][0]}, {"input_ids": batches[i][1]})
+        if mode == "graph":
+            tr.capture({"input_ids": full}, {"input_ids": qa})
+        for i in range(2, 6):
+            if mode == "graph":
+                tr.graph_step([({"input_ids": batches[i][0]}, {"input_ids": batches[i][1]})])
+            else:
+                tr.micro_step({"input_ids": batches[i][0]}, {"input_ids": batches[i][1]})
+        torch.cuda.synchronize()
+        assert tr.opt_step == 6
+        finals.append((tr.flat.param.clone(), tr.logged_scalars()))
+    (pe, se), (pg, sg) = finals
+    assert float((pe - pg).norm() / pe.norm()) < 1e-5
+    assert abs(se["loss"] - sg["loss"]) < 1e-4 * abs(se["loss"])
