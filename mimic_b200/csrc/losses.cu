@@ -2,6 +2,8 @@
 // (M), fused LM-loss cross-entropy forward+backward (C), and the on-device clip + AdamW step.
 // All are single launches over all layers / rows, 16-byte vectorised, streaming (L1 no-allocate)
 // loads and stores, persistent grid-stride over rows with grids sized from the SM count.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mimic {
@@ -152,9 +154,87 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const void* const* __r
   }
 }
 
+// Variant: one (layer, row) item per WARP.  Every warp runs an independent index -> load -> store chain, so
+// 32+ chains per SM overlap their latencies; 4 x 16-byte loads per array in flight per lane.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) mse_fwd_bwd_warp_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
+                                                               const T* __restrict__ hp,
+                                                               const int32_t* __restrict__ row_to_compact,
+                                                               const float* __restrict__ row_w,
+                                                               void* const* __restrict__ dh_ptrs, float grad_scale, int L,
+                                                               int rows, int N, int D, float* __restrict__ partial,
+                                                               unsigned int* __restrict__ counter, float* __restrict__ loss) {
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int chunks = D / 8;
+  const int64_t items = (int64_t)L * rows;
+  float acc = 0.f;
+  for (int64_t it = (int64_t)blockIdx.x * wpb + wib; it < items; it += (int64_t)gridDim.x * wpb) {
+    const int l = (int)(it / rows), r = (int)(it % rows);
+    const int c = row_to_compact[r];
+    T* dh = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) + (int64_t)r * D : nullptr;
+    if (c < 0) {
+      if (dh) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ch = lane; ch < chunks; ch += 32) Chunk<T>::store(dh + ch * 8, z);
+      }
+      continue;
+    }
+    const T* h = reinterpret_cast<const T*>(h_ptrs[l]) + (int64_t)r * h_row_stride;
+    const T* t = hp + ((int64_t)l * N + c) * D;
+    const float w = row_w[c];
+    const float gw = 2.f * w * grad_scale;
+    float s = 0.f;
+    for (int ch0 = lane; ch0 < chunks; ch0 += 32 * UNROLL) {
+      float a[UNROLL][8], b[UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int ch = ch0 + u * 32;
+        if (ch < chunks) {
+          Chunk<T>::load(h + ch * 8, a[u]);
+          Chunk<T>::load(t + ch * 8, b[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int ch = ch0 + u * 32;
+        if (ch < chunks) {
+          float g[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float df = a[u][e] - b[u][e];
+            s += df * df;
+            g[e] = gw * df;
+          }
+          if (dh) Chunk<T>::store(dh + ch * 8, g);
+        }
+      }
+    }
+    acc += w * s;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      loss[0] = tot;
+      *counter = 0u;
+    }
+  }
+}
+
 static int mse_grid(int L, int rows) {
   const int64_t items = (int64_t)L * rows;
-  const int64_t cap = (int64_t)num_sms() * 4;      // 64 registers x 256 threads: 4 resident CTAs per SM, one wave
+  const int64_t cap = (int64_t)num_sms() * 8;
   return (int)(items < cap ? items : cap);
 }
 
@@ -218,18 +298,28 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
     // pass 1: online max / sum
     float m = -INFINITY, s = 0.f;
     for (int i = threadIdx.x; i < head; i += blockDim.x) online_add(m, s, to_f32(x[i]));
-    for (int c = threadIdx.x; c < body; c += blockDim.x) {
-      float f[8];
-      load8(x + head + c * 8, f);     // default caching: pass 2 wants these lines back
-      float cm = f[0];
+    for (int c0 = threadIdx.x; c0 < body; c0 += blockDim.x * 4) {
+      float f[4][8];                   // 4 x 16-byte loads in flight per thread (default caching: pass 2 wants the lines back)
 #pragma unroll
-      for (int e = 1; e < 8; ++e) cm = fmaxf(cm, f[e]);
-      if (cm > m) {
-        s *= __expf(m - cm);
-        m = cm;
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < body) load8(x + head + c * 8, f[u]);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += __expf(f[e] - m);
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < body) {
+          float cm = f[u][0];
+#pragma unroll
+          for (int e = 1; e < 8; ++e) cm = fmaxf(cm, f[u][e]);
+          if (cm > m) {
+            s *= __expf(m - cm);
+            m = cm;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s += __expf(f[u][e] - m);
+        }
+      }
     }
     for (int i = tail0 + threadIdx.x; i < V; i += blockDim.x) online_add(m, s, to_f32(x[i]));
     // block combine of (m, s)
@@ -260,13 +350,23 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
         float pv = __expf(to_f32(x[i]) - gm) * inv_sum;
         dx[i] = from_f32<T>(gs * (pv - (i == label ? 1.f : 0.f)));
       }
-      for (int c = threadIdx.x; c < body; c += blockDim.x) {
-        float f[8];
-        const int base = head + c * 8;
-        load8(x + base, f);
+      for (int c0 = threadIdx.x; c0 < body; c0 += blockDim.x * 4) {
+        float f[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = gs * (__expf(f[e] - gm) * inv_sum - ((base + e) == label ? 1.f : 0.f));
-        Chunk<T>::store(dx + base, f);
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * blockDim.x;
+          if (c < body) load8(x + head + c * 8, f[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * blockDim.x;
+          if (c < body) {
+            const int base = head + c * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[u][e] = gs * (__expf(f[u][e] - gm) * inv_sum - ((base + e) == label ? 1.f : 0.f));
+            Chunk<T>::store(dx + base, f[u]);
+          }
+        }
       }
       for (int i = tail0 + threadIdx.x; i < V; i += blockDim.x) {
         float pv = __expf(to_f32(x[i]) - gm) * inv_sum;
@@ -375,7 +475,17 @@ extern "C" int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride
   const int grid = mse_grid(L, rows);
   float* partial = static_cast<float*>(workspace) + 4;
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
-  if (h_dtype == MIMIC_BF16)
+  static const int variant = getenv("MIMIC_MSE_VARIANT") ? atoi(getenv("MIMIC_MSE_VARIANT")) : 3;   // 3 measured best (79% of HBM peak)
+  if (h_dtype == MIMIC_BF16 && variant == 1)
+    mse_fwd_bwd_warp_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                                    row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_BF16 && variant == 2)
+    mse_fwd_bwd_warp_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                                    row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_BF16 && variant == 3)
+    mse_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_BF16)
     mse_fwd_bwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
                                                                row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
   else if (h_dtype == MIMIC_F32)
@@ -403,7 +513,7 @@ extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
   float* row_loss = static_cast<float*>(workspace) + 4;
-  const int grid = R < num_sms() * 4 ? R : num_sms() * 4;
+  const int grid = R < num_sms() * 4 ? R : num_sms() * 4;   // measured: more CTAs beat a smaller L2 footprint
   if (dtype == MIMIC_BF16)
     ce_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)logits, logits_row_stride, labels,
                                                            (__nv_bfloat16*)dlogits, grad_scale, R, V, n_kept, loss, row_loss, counter);

@@ -14,6 +14,7 @@ for one process per GPU:
 from __future__ import annotations
 
 import math
+from contextlib import nullcontext
 from typing import Dict, Optional
 
 import torch
@@ -88,10 +89,13 @@ class MimicTrainer:
         self._static = None
         # Every step (eager warm-up, capture, replay) runs on this one non-default stream: autograd binds each
         # leaf's gradient accumulator to the stream of its first use, and a capture only accepts same-stream edges.
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def _on_stream(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else nullcontext()
 
     def micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             return self._micro_step(inputs, query_inputs)
 
     def _micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
@@ -125,8 +129,9 @@ class MimicTrainer:
                        max_norm=self.clip, sumsq=self.sumsq)
 
     def optimizer_step(self) -> None:
-        self._advance_schedule()
-        self._device_optimizer_step()
+        with self._on_stream():
+            self._advance_schedule()
+            self._device_optimizer_step()
 
     # ---- whole-step CUDA graph -----------------------------------------------------------------------
     def capture(self, inputs: Optional[dict], query_inputs: dict) -> None:
@@ -135,7 +140,7 @@ class MimicTrainer:
         launch-bound on a busy host (~4000 small launches); replay removes the host from the loop.  Call after
         a few eager steps (allocations, hook installation and the forward replacement must have happened)."""
         assert self.micro % self.accum == 0, "capture at an optimizer-step boundary"
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             self._capture(inputs, query_inputs)
 
     def _capture(self, inputs, query_inputs) -> None:
@@ -168,7 +173,7 @@ class MimicTrainer:
         """Replay the captured step on `accum` new micro-batches [(inputs, query_inputs), ...] of the captured
         shapes (host or device tensors; copied into the static buffers)."""
         assert self._graph is not None, "call capture() first"
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             self._graph_step(batches)
 
     def _graph_step(self, batches) -> None:
@@ -183,7 +188,7 @@ class MimicTrainer:
 
     def logged_scalars(self) -> Dict[str, float]:
         """Mean over ranks of the loss terms of the last optimizer step (one D2H read)."""
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             vals = (self.flat.scalars / self.world).tolist()
         return dict(zip(("loss", "ce_loss", "ffn_mse_loss"), vals))
 
