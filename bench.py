@@ -147,6 +147,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MIMIC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
@@ -236,10 +237,19 @@ def main():
     tokens_per_step = B * (S + T) * world
     value = tokens_per_step / (ms / args.steps / 1e3)
     e2e = tokens_per_step / (ms_e2e / args.steps / 1e3)
-    if rank != 0:
+    def finish():
+        # a captured graph that holds NCCL kernels can stall process-group teardown: drop it first, then leave
+        # without running destructors (the JSON line is already flushed)
+        trainer._graph = None
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    if rank != 0:
+        finish()
 
     peaks = load_peaks()
     H, d, L = cfgm.num_attention_heads, cfgm.head_dim, cfgm.num_hidden_layers
@@ -287,8 +297,7 @@ def main():
                                 "sample": f"{stp['n_layers']} of {stp['model_layers']} decoder layers at the full token "
                                           f"shape, per-layer time x depth + LM head/CE once (oracle/cpu_step.py)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
