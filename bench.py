@@ -34,6 +34,10 @@ WORKLOADS = {
 }
 
 
+def workload_name(key: str) -> str:
+    return f"{key} shapes, MimIC shifted attention + LAYER_WISE_MSE + LM loss train step, synthetic VQAv2-like batch"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,7 +113,9 @@ def run_reference(args, wl):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * last["tokens"] / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: wl[k] for k in ("B", "S_ctx", "T_q")}},
+            "config": {"workload": workload_name(args.workload), "B_per_gpu": wl["B"], "S_ctx": wl["S_ctx"], "T_q": wl["T_q"],
+                       "layers": last["model_layers"], "parallelism": f"dp{args.gpus}",
+                       "note": "reference CPU path: rank 0 only, the same per-GPU micro-batch"},
             "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -147,7 +153,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MIMIC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL prints its version banner to STDOUT at levels VERSION and WARN: keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("MIMIC_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["MIMIC_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
@@ -279,8 +288,7 @@ def main():
         "metric": "MimIC train tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload} shapes, MimIC shifted attention + LAYER_WISE_MSE + LM loss train step, "
-                               f"synthetic VQAv2-like batch", "B_per_gpu": B, "S_ctx": S, "T_q": T,
+        "config": {"workload": workload_name(args.workload), "B_per_gpu": B, "S_ctx": S, "T_q": T,
                    "layers": L, "attn_impl": mimic_b200._lib.last_attn_impl(), "parallelism": f"dp{world}",
                    "step_launch": "whole-step CUDA graph replay" if use_graph else "eager",
                    "eager_ms_per_step": ms_eager / n_eager,
