@@ -20,6 +20,7 @@
 #include "attn_common.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
+#include "tc_softmax.cuh"
 
 namespace mimic {
 namespace tc {
@@ -162,7 +163,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (elect_one()) {
           const uint32_t k_lo = k_lo0 + ks * (TILE_BYTES >> 4);
           const uint32_t d_s = tmem_base + st * BN;
-          for (int rep = 0; rep <= p.debug_flags; ++rep) {   // debug_flags > 0: re-issue QK^T (timing experiments)
+          for (int rep = 0; rep <= (p.debug_flags & 255); ++rep) {   // debug_flags > 0: re-issue QK^T (timing experiments)
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t koff = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
@@ -189,6 +190,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             // A: P_j in TMEM, 16 bf16 of K per step = 8 columns; B: V_j [keys][d], 16 keys = 2048 B per step
             const uint32_t v_lo = v_lo0 + vs * (TILE_BYTES >> 4);
             const uint32_t a_p = tmem_base + st * BN;
+            for (int rep = 0; rep < ((p.debug_flags >> 8) & 255); ++rep) {   // debug: re-issue PV (timing experiments only)
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+            }
             if (j > 0) {
 #pragma unroll
               for (int k = 0; k < BN / 16; ++k) mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
@@ -259,6 +264,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         all_vis = all_vis && (vw[i] == 0xFFFFFFFFu);
         any_exc = any_exc || (xw[i] != 0u);
       }
+      const bool all_vis_w = __all_sync(0xffffffffu, all_vis);    // warp-uniform: mask-free fast path
       if (j <= jd) {
         float s[128];
         tmem_ld32(taddr, *reinterpret_cast<float(*)[32]>(s));
@@ -266,10 +272,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_ld32(taddr + 64, *reinterpret_cast<float(*)[32]>(s + 64));
         tmem_ld32(taddr + 96, *reinterpret_cast<float(*)[32]>(s + 96));
         tc_wait_ld();
+        for (int rep = 0; rep < (p.debug_flags >> 16); ++rep) {    // debug: extra TMEM reads (timing experiments only)
+          tmem_ld32(taddr, *reinterpret_cast<float(*)[32]>(s));
+          tmem_ld32(taddr + 32, *reinterpret_cast<float(*)[32]>(s + 32));
+          tmem_ld32(taddr + 64, *reinterpret_cast<float(*)[32]>(s + 64));
+          tmem_ld32(taddr + 96, *reinterpret_cast<float(*)[32]>(s + 96));
+          tc_wait_ld();
+        }
         float mv = -INFINITY;
-        if (all_vis) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c) mv = fmaxf(mv, s[c]);
+        if (all_vis_w) {
+          mv = row_max128(s);
         } else {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -303,24 +315,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         // P = exp2(s*scale2 - m_c) on visible keys -> bf16 pairs -> TMEM (first 64 columns of this S buffer)
         const float neg_m = (m_c == -INFINITY) ? 0.f : -m_c;
-        float rowsum = 0.f;
+        if (all_vis_w) {
+          l_c += exp_pack_store128(s, scale2, neg_m, taddr);
+        } else {
+          float rowsum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t pk[16];
+          for (int i = 0; i < 4; ++i) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int c2 = 0; c2 < 16; ++c2) {
-            const int c = 32 * i + 2 * c2;
-            float p0 = ex2(fmaf(s[c], scale2, neg_m)), p1 = ex2(fmaf(s[c + 1], scale2, neg_m));
-            if (!all_vis) {
+            for (int c2 = 0; c2 < 16; ++c2) {
+              const int c = 32 * i + 2 * c2;
+              float p0 = ex2(fmaf(s[c], scale2, neg_m)), p1 = ex2(fmaf(s[c + 1], scale2, neg_m));
               if (!((vw[i] >> (2 * c2)) & 1u)) p0 = 0.f;
               if (!((vw[i] >> (2 * c2 + 1)) & 1u)) p1 = 0.f;
+              rowsum += p0 + p1;
+              pk[c2] = pack_bf16(p0, p1);
             }
-            rowsum += p0 + p1;
-            pk[c2] = pack_bf16(p0, p1);
+            tmem_st16(taddr + 16 * i, pk);
           }
-          tmem_st16(taddr + 16 * i, pk);
+          l_c += rowsum;
         }
-        l_c += rowsum;
         if (any_exc) {                                 // excluded keys inside a tile that also has visible ones
           float mx = -INFINITY;
 #pragma unroll
@@ -343,19 +357,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           float s[32];
           tmem_ld32(taddr + 32 * i, s);
           tc_wait_ld();
-          if (xw[i] != 0u) {
+          if (__all_sync(0xffffffffu, xw[i] == 0xFFFFFFFFu)) {
+            const float mx_new = fmaxf(m_x, max32(s) * scale2);
+            l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + expsum32(s, scale2, -mx_new);
+            m_x = mx_new;
+          } else if (xw[i] != 0u) {
             float mx = -INFINITY;
-            const bool full = xw[i] == 0xFFFFFFFFu;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (full || ((xw[i] >> c) & 1u)) mx = fmaxf(mx, s[c]);
+              if ((xw[i] >> c) & 1u) mx = fmaxf(mx, s[c]);
             mx *= scale2;
             const float mx_new = fmaxf(m_x, mx);
             float es = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float e = ex2(fmaf(s[c], scale2, -mx_new));
-              es += (full || ((xw[i] >> c) & 1u)) ? e : 0.f;
+              es += ((xw[i] >> c) & 1u) ? e : 0.f;
             }
             l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + es;
             m_x = mx_new;
@@ -432,7 +449,9 @@ int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query 
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
-  if (p.T > BM && getenv("MIMIC_FWD_V1") == nullptr) return fwd2(p, st);
+  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2": force the single-tile / ping-pong kernel
+  const bool use2 = force ? (force[0] == '2') : (p.T > BM);
+  if (use2 && p.T > BM) return fwd2(p, st);
   AttnParams pd = p;
   if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pd.debug_flags = atoi(e);
   CUtensorMap tq, tk, tv;

@@ -15,6 +15,7 @@
 #include "attn_common.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
+#include "tc_softmax.cuh"
 
 namespace mimic {
 namespace tc {
@@ -288,8 +289,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_wait_ld();
         float mv = -INFINITY;
         if (all_vis) {
-#pragma unroll
-          for (int c = 0; c < 128; c += 2) mv = fmaxf(mv, fmaxf(s[c], s[c + 1]));
+          mv = row_max128(s);
         } else {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -322,23 +322,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         const float neg_m = (m_c == -INFINITY) ? 0.f : -m_c;
         if (all_vis) {
-          // P = exp2(s*scale2 - m_c): packed fp32x2 FMA / ADD halve the non-MUFU instruction count
-          const float2 negv = make_float2(neg_m, neg_m);
-          float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int c2 = 0; c2 < 16; ++c2) {
-              const int c = 32 * i + 2 * c2;
-              const float2 a = __ffma2_rn(make_float2(s[c], s[c + 1]), scale2v, negv);
-              const float2 e = make_float2(ex2(a.x), ex2(a.y));
-              sum2 = __fadd2_rn(sum2, e);
-              pk[c2] = pack_bf16(e.x, e.y);
-            }
-            tmem_st16(t_S + 16 * i, pk);
-          }
-          l_c += sum2.x + sum2.y;
+          l_c += exp_pack_store128(s, scale2, neg_m, t_S);      // packed fp32x2 FMA/ADD, 4 independent sum chains
         } else {
           float rowsum = 0.f;
 #pragma unroll
@@ -382,19 +366,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_ld32(t_S + 32 * i, s);
           tc_wait_ld();
           if (all_exc) {
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(s[c], s[c + 1]));
-            mx *= scale2;
-            const float mx_new = fmaxf(m_x, mx);
-            const float2 negv = make_float2(-mx_new, -mx_new);
-            float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float2 a = __ffma2_rn(make_float2(s[c], s[c + 1]), scale2v, negv);
-              sum2 = __fadd2_rn(sum2, make_float2(ex2(a.x), ex2(a.y)));
-            }
-            l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + sum2.x + sum2.y;
+            const float mx_new = fmaxf(m_x, max32(s) * scale2);
+            l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + expsum32(s, scale2, -mx_new);
             m_x = mx_new;
           } else if (xw[i] != 0u) {
             float mx = -INFINITY;

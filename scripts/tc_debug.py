@@ -159,3 +159,7 @@ if __name__ == "__main__":
         perf(4, 32, 32, 4096, False)
         perf(4, 32, 32, 4096, True)
         perf(2, 32, 32, 8192, True)
+    if which == "cta":
+        perf(64, 32, 32, 128, False)      # 2048 CTAs x 1 tile: per-CTA fixed cost
+        perf(32, 32, 32, 256, False)      # 2048 CTAs x avg 1.5 tiles (v1) / 1024 CTAs x 3 (v2)
+        perf(16, 32, 32, 512, False)
