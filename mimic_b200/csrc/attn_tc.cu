@@ -446,12 +446,14 @@ bool supports(const AttnParams& p, bool backward) {
 }
 
 int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query tiles per CTA
+int fwd64(const AttnParams& p, cudaStream_t st);  // attn_tc_fwd64.cu: 64-key tiles, two CTAs per SM
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
-  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2": force the single-tile / ping-pong kernel
-  const bool use2 = force ? (force[0] == '2') : (p.T > BM);
-  if (use2 && p.T > BM) return fwd2(p, st);
+  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3": single-tile / ping-pong / 64-key two-CTA kernel
+  const int kern = force ? atoi(force) : 3;             // measured on B200: 3 is the fastest at every T
+  if (kern == 3 && (size_t)((p.S + 63) / 64) * 8 < 16000) return fwd64(p, st);
+  if (kern == 2 && p.T > BM) return fwd2(p, st);
   AttnParams pd = p;
   if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pd.debug_flags = atoi(e);
   CUtensorMap tq, tk, tv;

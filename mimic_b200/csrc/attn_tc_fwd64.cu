@@ -1,0 +1,418 @@
+// Shifted self-attention forward, 64-key tiles, TWO CTAs PER SM.
+// Same math / masks / outputs as attn_fwd_tc_kernel (attn_tc.cu).  Halving the key tile halves the shared
+// memory (96 KB) and tensor memory (256 columns) of a CTA, so two CTAs share an SM: one CTA's prologue
+// (barrier init, TMEM alloc, first TMA round trip, pipeline fill) and epilogue (normalise, store, dealloc)
+// — ~6 us that a lone CTA leaves the tensor pipe idle — overlap with the other CTA's main loop, and the SM
+// runs 8 softmax warps (two per sub-partition) instead of 4.
+//   TMEM (256 cols): S0 [0,64) S1 [64,128) O [128,256);  P_j = first 32 cols of S[j&1].
+//   smem: Q 32 KB | K ring 2 x 16 KB | V ring 2 x 16 KB | barriers, w, shift, key bits.
+#include <cuda.h>
+
+#include "attn_common.cuh"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+#include "tc_softmax.cuh"
+
+namespace mimic {
+namespace tc {
+
+using namespace ptx;
+
+namespace f64 {
+constexpr int BM = 128, BN = 64, HD = 128, NKV = 2;
+constexpr int Q_HALF = 128 * 128;            // [128 rows][128 B]
+constexpr int Q_TILE = 2 * Q_HALF;           // 32 KB
+constexpr int KV_HALF = BN * 128;            // [64 keys][128 B] = 8 KB
+constexpr int KV_TILE = 2 * KV_HALF;         // 16 KB
+constexpr int THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr float RESCALE_THRESHOLD = 8.f;
+constexpr int OFF_Q = 0, OFF_K = Q_TILE, OFF_V = OFF_K + NKV * KV_TILE, OFF_BAR = OFF_V + NKV * KV_TILE;
+constexpr int OFF_TMEM = OFF_BAR + 24 * 8, OFF_W = OFF_TMEM + 16, OFF_SHIFT = OFF_W + 512, OFF_KBITS = OFF_SHIFT + 512;
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, SOFT_DONE = 11, PV_DONE = 13, O_FULL = 14 };
+constexpr uint32_t IDESC_QK = idesc_bf16(BM, BN, 0, 0);
+constexpr uint32_t IDESC_PV = idesc_bf16(BM, HD, 0, 1);
+constexpr uint32_t TMEM_COLS = 256, TM_O = 128;
+inline size_t smem_bytes(int S) { return OFF_KBITS + (size_t)((S + BN - 1) / BN) * 8; }
+}  // namespace f64
+
+__device__ __forceinline__ uint32_t low_bits3(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+__global__ void __launch_bounds__(f64::THREADS, 2)
+attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v, AttnParams p) {
+  using namespace f64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("[mimic tcgen05] dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem + OFF_Q;
+  uint8_t* sK = smem + OFF_K;
+  uint8_t* sV = smem + OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  float* w_s = reinterpret_cast<float*>(smem + OFF_W);
+  float* shift_s = reinterpret_cast<float*>(smem + OFF_SHIFT);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + OFF_KBITS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;          // heaviest (latest) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.Hkv);
+  const int T = p.T, S = p.S, off = p.S - p.T;
+  const int t0 = qt * BM;
+  const int n_tiles = (S + BN - 1) / BN;
+  int jd = n_tiles - 1;
+  if (p.causal) {
+    const int smax = min(t0 + BM - 1, T - 1) + off;
+    jd = smax < 0 ? -1 : min(n_tiles - 1, smax / BN);
+  }
+  const int n = p.active ? n_tiles : jd + 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(&bars[Q_FULL], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars[K_FULL + i], 1);
+        mbar_init(&bars[K_EMPTY + i], 1);
+        mbar_init(&bars[V_FULL + i], 1);
+        mbar_init(&bars[V_EMPTY + i], 1);
+        mbar_init(&bars[S_FULL + i], 1);
+        mbar_init(&bars[SOFT_DONE + i], 128);
+      }
+      mbar_init(&bars[PV_DONE], 1);
+      mbar_init(&bars[O_FULL], 1);
+      fence_barrier_init();
+      prefetch_tmap(&tm_q);
+      prefetch_tmap(&tm_k);
+      prefetch_tmap(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  } else if (warp >= 2) {
+    const int st = threadIdx.x - 64;
+    if (p.active) {
+      w_s[st] = p.w[h * HD + st];
+      shift_s[st] = p.shift[h * HD + st];
+    }
+    const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * S : nullptr;
+    for (int wi = warp - 2; wi < n_tiles * 2; wi += 4) {
+      const int s = wi * 32 + lane;
+      const bool ok = s < S && (km == nullptr || km[s] != 0);
+      const uint32_t word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) kbits[wi] = word;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + TM_O;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(&bars[Q_FULL], Q_TILE);
+      tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, t0, h, b);
+      tma_load_4d(sQ + Q_HALF, &tm_q, &bars[Q_FULL], 64, t0, h, b);
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 100 + st);
+        mbar_expect_tx(&bars[K_FULL + st], KV_TILE);
+        tma_load_4d(sK + st * KV_TILE, &tm_k, &bars[K_FULL + st], 0, j * BN, kvh, b);
+        tma_load_4d(sK + st * KV_TILE + KV_HALF, &tm_k, &bars[K_FULL + st], 64, j * BN, kvh, b);
+        if (j <= jd) {
+          mbar_wait(&bars[V_EMPTY + st], ph ^ 1, 110 + st);
+          mbar_expect_tx(&bars[V_FULL + st], KV_TILE);
+          tma_load_4d(sV + st * KV_TILE, &tm_v, &bars[V_FULL + st], 0, j * BN, kvh, b);
+          tma_load_4d(sV + st * KV_TILE + KV_HALF, &tm_v, &bars[V_FULL + st], 64, j * BN, kvh, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    if (n > 0) {
+      constexpr uint32_t HI = desc_hi_sw128(1024);
+      const uint32_t q_lo = desc_lo(smem_u32(sQ), 16), k_lo0 = desc_lo(smem_u32(sK), 16);
+      const uint32_t v_lo0 = desc_lo(smem_u32(sV), KV_HALF);            // V as MN-major B: d halves 8 KB apart
+      mbar_wait(&bars[Q_FULL], 0, 200);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 210 + st);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t k_lo = k_lo0 + st * (KV_TILE >> 4);
+          const uint32_t d_s = tmem_base + st * BN;
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t qoff = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4, koff = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4;
+            if (k == 0) mma_ss_c<false>(d_s, desc64(HI, q_lo + qoff), desc64(HI, k_lo + koff), IDESC_QK);
+            else mma_ss_c<true>(d_s, desc64(HI, q_lo + qoff), desc64(HI, k_lo + koff), IDESC_QK);
+          }
+          tc_commit(&bars[K_EMPTY + st]);
+          tc_commit(&bars[S_FULL + st]);
+        }
+        __syncwarp();
+      };
+      issue_qk(0);
+      if (n > 1) issue_qk(1);
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        mbar_wait(&bars[SOFT_DONE + st], (j >> 1) & 1, 220 + st);
+        tc_fence_after();
+        if (j <= jd) {
+          mbar_wait(&bars[V_FULL + st], (j >> 1) & 1, 230 + st);
+          tc_fence_after();
+          if (elect_one()) {
+            // A: P_j in TMEM (64 keys = 32 packed columns, 8 per K step); B: V_j [64 keys][d], 16 keys = 2 KB per step
+            const uint32_t v_lo = v_lo0 + st * (KV_TILE >> 4);
+            const uint32_t a_p = tmem_base + st * BN;
+            if (j > 0) {
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) {
+                if (k == 0) mma_ts_c<false>(tmem_O, a_p, desc64(HI, v_lo), IDESC_PV);
+                else mma_ts_c<true>(tmem_O, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+              }
+            }
+            tc_commit(&bars[V_EMPTY + st]);
+            tc_commit(&bars[PV_DONE]);
+          }
+          __syncwarp();
+        }
+        if (j + 2 < n) issue_qk(j + 2);
+      }
+      if (elect_one()) tc_commit(&bars[O_FULL]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one query row per thread =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int t = t0 + r;
+    const bool row_ok = t < T;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float scale2 = p.scale * LOG2E;
+
+    float z1 = 0.f;
+    mbar_wait(&bars[Q_FULL], 0, 300);
+    if (p.active) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sQ + hf * Q_HALF + r * 128 + ((c ^ (r & 7)) << 4));
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(hh[e]);
+            const int col = hf * 64 + c * 8 + e * 2;
+            z1 = fmaf(f.x, w_s[col], z1);
+            z1 = fmaf(f.y, w_s[col + 1], z1);
+          }
+        }
+      z1 += p.bias[h];
+    }
+
+    float m_c = -INFINITY, l_c = 0.f, m_x = -INFINITY, l_x = 0.f;   // log2 domain
+    for (int j = 0; j < n; ++j) {
+      const int st = j & 1;
+      mbar_wait(&bars[S_FULL + st], (j >> 1) & 1, 310 + st);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_off + st * BN;
+      const int key0 = j * BN;
+      uint32_t vw[2], xw[2];
+      bool all_vis_t = row_ok, any_exc_t = false, all_exc_t = true;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t inr = low_bits3(S - key0 - 32 * i);
+        const uint32_t cz = p.causal ? low_bits3(t + off - key0 - 32 * i + 1) : 0xFFFFFFFFu;
+        vw[i] = row_ok ? (kbits[j * 2 + i] & cz) : 0u;
+        xw[i] = (p.active && row_ok) ? (inr & ~vw[i]) : 0u;
+        all_vis_t = all_vis_t && (vw[i] == 0xFFFFFFFFu);
+        any_exc_t = any_exc_t || (xw[i] != 0u);
+        all_exc_t = all_exc_t && (xw[i] == 0xFFFFFFFFu);
+      }
+      const bool all_vis = __all_sync(0xffffffffu, all_vis_t);
+      const bool any_exc = __any_sync(0xffffffffu, any_exc_t);
+      float s[64];
+      tmem_ld32(taddr, *reinterpret_cast<float(*)[32]>(s));
+      tmem_ld32(taddr + 32, *reinterpret_cast<float(*)[32]>(s + 32));
+      tc_wait_ld();
+      if (j <= jd) {
+        float mv = -INFINITY;
+        if (all_vis) {
+          mv = row_max64(s);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if ((vw[c >> 5] >> (c & 31)) & 1u) mv = fmaxf(mv, s[c]);
+        }
+        mv *= scale2;
+        const float m_new = fmaxf(m_c, mv);
+        const bool need = (m_c != -INFINITY) && (m_new > m_c + RESCALE_THRESHOLD);
+        if (m_c == -INFINITY) m_c = m_new;
+        if (__any_sync(0xffffffffu, need)) {            // lazy rescale of O and l_c (warp-collective TMEM ops)
+          const float alpha = need ? ex2(m_c - m_new) : 1.f;
+          if (j > 0) {
+            mbar_wait(&bars[PV_DONE], (j - 1) & 1, 320);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float o[32];
+              tmem_ld32(tmem_O + lane_off + 32 * i, o);
+              tc_wait_ld();
+              uint32_t ou[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) ou[c] = __float_as_uint(o[c] * alpha);
+              tmem_st32(tmem_O + lane_off + 32 * i, ou);
+            }
+          }
+          if (need) {
+            l_c *= alpha;
+            m_c = m_new;
+          }
+        }
+        const float neg_m = (m_c == -INFINITY) ? 0.f : -m_c;
+        if (all_vis) {
+          l_c += exp_pack_store64(s, scale2, neg_m, taddr);
+        } else {
+          float rowsum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int c2 = 0; c2 < 16; ++c2) {
+              const int c = 32 * i + 2 * c2;
+              float p0 = ex2(fmaf(s[c], scale2, neg_m)), p1 = ex2(fmaf(s[c + 1], scale2, neg_m));
+              if (!((vw[i] >> (2 * c2)) & 1u)) p0 = 0.f;
+              if (!((vw[i] >> (2 * c2 + 1)) & 1u)) p1 = 0.f;
+              rowsum += p0 + p1;
+              pk[c2] = pack_bf16(p0, p1);
+            }
+            tmem_st16(taddr + 16 * i, pk);
+          }
+          l_c += rowsum;
+        }
+        if (any_exc) {                                 // excluded keys inside a tile that also has visible ones
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if ((xw[c >> 5] >> (c & 31)) & 1u) mx = fmaxf(mx, s[c]);
+          mx *= scale2;
+          const float mx_new = fmaxf(m_x, mx);
+          float es = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if ((xw[c >> 5] >> (c & 31)) & 1u) es += ex2(fmaf(s[c], scale2, -mx_new));
+          l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + es;
+          m_x = mx_new;
+        }
+        tc_wait_st();
+      } else if (__all_sync(0xffffffffu, all_exc_t)) {
+        // tile above the causal diagonal, every key excluded: row-sum of exp only
+        const float mx_new = fmaxf(m_x, row_max64(s) * scale2);
+        l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) +
+              expsum32(*reinterpret_cast<const float(*)[32]>(s), scale2, -mx_new) +
+              expsum32(*reinterpret_cast<const float(*)[32]>(s + 32), scale2, -mx_new);
+        m_x = mx_new;
+      } else if (any_exc) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if ((xw[c >> 5] >> (c & 31)) & 1u) mx = fmaxf(mx, s[c]);
+        mx *= scale2;
+        const float mx_new = fmaxf(m_x, mx);
+        float es = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const float e = ex2(fmaf(s[c], scale2, -mx_new));
+          es += ((xw[c >> 5] >> (c & 31)) & 1u) ? e : 0.f;
+        }
+        l_x = l_x * ((m_x == -INFINITY) ? 0.f : ex2(m_x - mx_new)) + es;
+        m_x = mx_new;
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[SOFT_DONE + st]);
+    }
+
+    // ---- epilogue ----
+    const float inv = l_c > 0.f ? 1.f / l_c : 0.f;
+    const float lse_c = l_c > 0.f ? (m_c + log2f(l_c)) * LN2 : -INFINITY;
+    float mu = 0.f, lse_full = 0.f;
+    if (p.active) {
+      const float lse_x = l_x > 0.f ? (m_x + log2f(l_x)) * LN2 : -INFINITY;
+      const float hi = fmaxf(lse_c, lse_x), lo = fminf(lse_c, lse_x);
+      lse_full = (lo == -INFINITY) ? hi : hi + log1pf(__expf(lo - hi));
+      mu = 1.f / (1.f + __expf(lse_full - z1));
+    }
+    if (jd >= 0) {
+      mbar_wait(&bars[O_FULL], 0, 330);
+      tc_fence_after();
+    }
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_sb + (int64_t)t * p.o_st + (int64_t)h * p.o_sh;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float o[32];
+      if (jd >= 0) {
+        tmem_ld32(tmem_O + lane_off + 32 * i, o);
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] = 0.f;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = 32 * i + 8 * c8 + e;
+            f[e] = o[8 * c8 + e] * inv + (p.active ? mu * shift_s[c] : 0.f);
+          }
+          store8(orow + 32 * i + 8 * c8, f);
+        }
+      }
+    }
+    if (row_ok) {
+      const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
+      p.lse_c[ridx] = lse_c;
+      if (p.active) {
+        p.lse_full[ridx] = lse_full;
+        p.mu[ridx] = mu;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int fwd64(const AttnParams& p, cudaStream_t st) {
+  using namespace f64;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BM))) return rc;
+  if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
+  if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, BN))) return rc;
+  const size_t smem = smem_bytes(p.S);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((p.T + BM - 1) / BM, p.H, p.B);
+  attn_fwd_tc64_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, p);
+  MIMIC_LAUNCH_OK("attn_fwd_tc64_kernel");
+  return MIMIC_OK;
+}
+
+}  // namespace tc
+}  // namespace mimic
