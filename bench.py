@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=1, help="decoder layers in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="run this many eager steps and exit (for ncu launch lists; no JSON line)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -175,6 +177,17 @@ def main():
     full_pin, qa_pin = full_h.pin_memory(), qa_h.pin_memory()
     full_d, qa_d = full_h.to(dev), qa_h.to(dev)
 
+    def finish():
+        # a captured graph that holds NCCL kernels can stall process-group teardown: drop it first, then leave
+        # without running destructors (the JSON line is already flushed)
+        trainer._graph = None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     use_graph = not args.no_graph
 
     def step_eager():
@@ -213,6 +226,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    if args.profile_steps:
+        for _ in range(args.profile_steps):
+            step_eager()
+        torch.cuda.synchronize()
+        print(f"profile: {args.profile_steps} eager steps, {ops.launch_count} launches of our kernels", file=sys.stderr)
+        finish()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                     # started before warm-up: process start-up stays out of the timed region
@@ -246,17 +265,6 @@ def main():
     tokens_per_step = B * (S + T) * world
     value = tokens_per_step / (ms / args.steps / 1e3)
     e2e = tokens_per_step / (ms_e2e / args.steps / 1e3)
-    def finish():
-        # a captured graph that holds NCCL kernels can stall process-group teardown: drop it first, then leave
-        # without running destructors (the JSON line is already flushed)
-        trainer._graph = None
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
-
     if rank != 0:
         finish()
 

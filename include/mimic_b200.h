@@ -37,6 +37,9 @@ MIMIC_API int mimic_abi_version(void);
 MIMIC_API const char* mimic_last_error(void);
 /* name of the kernel family the last mimic_shifted_attn_* call on this thread launched */
 MIMIC_API const char* mimic_last_attn_impl(void);
+/* Debug: device buffer of n_entries uint64 that CTA (0,0,0) of the tcgen05 backward kernel fills with
+ * (tag << 48 | clock) records — a per-role timeline for tuning.  NULL disables (default). */
+MIMIC_API void mimic_debug_set_trace(void* device_u64_buffer, size_t n_entries);
 
 /* ------------------------------------------------------------------------------------------
  * Shifted self-attention.

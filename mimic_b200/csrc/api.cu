@@ -20,6 +20,12 @@ void set_attn_impl(const char* name) {
   g_impl[sizeof(g_impl) - 1] = 0;
 }
 
+static unsigned long long* g_trace = nullptr;
+static size_t g_trace_cap = 0;
+unsigned long long* debug_trace_buffer() { return g_trace; }
+size_t debug_trace_capacity() { return g_trace_cap; }
+void set_trace(void* buf, size_t n) { g_trace = static_cast<unsigned long long*>(buf); g_trace_cap = n; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -37,4 +43,5 @@ extern "C" {
 int mimic_abi_version(void) { return MIMIC_ABI_VERSION; }
 const char* mimic_last_error(void) { return mimic::g_err; }
 const char* mimic_last_attn_impl(void) { return mimic::g_impl; }
+void mimic_debug_set_trace(void* device_u64_buffer, size_t n_entries) { mimic::set_trace(device_u64_buffer, n_entries); }
 }

@@ -24,8 +24,12 @@ struct AttnParams {
   float *dshift, *dw, *dbias;
   float *dq_acc, *delta_ws, *dz_ws;
   int debug_flags = 0;
+  unsigned long long* trace = nullptr;   // optional in-kernel timeline (mimic_debug_set_trace), CTA (0,0,0) only
   float dq_seed_mul = 1.f, dq_out_mul = 1.f;   // dq_acc seed = dz*w*seed_mul; dq = dq_acc*out_mul
 };
+
+unsigned long long* debug_trace_buffer();
+size_t debug_trace_capacity();
 
 namespace simt {
 int fwd(const AttnParams& p, cudaStream_t st);

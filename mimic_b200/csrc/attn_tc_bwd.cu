@@ -46,7 +46,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + NQS * Q_TILE, OFF_DS = OFF_DO + NQS * Q_TILE,
               OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 2 * BQ * 16,
-              OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16 + 1024;
+              OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16;
 
 enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, N_BARS = 16 };
 
@@ -62,8 +62,12 @@ __global__ void __launch_bounds__(bw::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnParams p) {
   using namespace bw;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // address the dynamic window directly (no pointer rounding through integers): keeps every access LDS/STS
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("[mimic tcgen05] dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sK = smem + OFF_K;
   uint8_t* sV = smem + OFF_V;
   uint8_t* sQ = smem + OFF_Q;
@@ -76,6 +80,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  // timeline trace (debug): role r writes record k of iteration i at trace[(i * 8 + r) * 8 + k]
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto stamp = [&](int role, int i, int k) {
+    if (tracing && i < 24) p.trace[(i * 8 + role) * 8 + k] = clock64();
+  };
   const int G = p.H / p.Hkv;
   const int T = p.T, S = p.S, off = p.S - p.T;
   const int s0 = kt * BN;
@@ -130,6 +139,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int h = kvh * G + i / nq, qt = qt_first + i % nq;
         const bool nc = need_c(qt);
         if (!(p.debug_flags & 8)) mbar_wait(&bars[QDO_EMPTY + st], ((i / NQS) & 1) ^ 1, 100 + st);
+        stamp(0, i, 0);
         mbar_expect_tx(&bars[QDO_FULL + st], nc ? 2 * Q_TILE : Q_TILE);
         tma_load_4d(sQ + st * Q_TILE, &tm_q, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
         tma_load_4d(sQ + st * Q_TILE + Q_HALF, &tm_q, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
@@ -155,7 +165,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int qt = qt_first + i % nq;
         const bool nc = need_c(qt);
         if (!(p.debug_flags & 16)) mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
+        if (lane == 0) stamp(1, i, 0);
         if (!(p.debug_flags & 2)) mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
+        if (lane == 0) stamp(1, i, 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t q_km = q_km0 + qs * (Q_TILE >> 4), do_km = do_km0 + qs * (Q_TILE >> 4);
@@ -178,6 +190,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tc_commit(&bars[S_FULL + st]);
         }
         __syncwarp();
+        if (lane == 0) stamp(1, i, 2);
       };
       bool dv_started = false;
       issue_sdp(0);
@@ -187,6 +200,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const bool nc = need_c(qt);
         if (i + 1 < n) issue_sdp(i + 1);
         mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
+        if (lane == 0) stamp(1, i, 3);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
@@ -230,6 +244,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tc_commit(&bars[DQ_FULL + st]);
         }
         __syncwarp();
+        if (lane == 0) stamp(1, i, 4);
         if (nc) dv_started = true;
       }
       if (elect_one()) tc_commit(&bars[DKV_FULL]);
@@ -249,8 +264,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const bool key_ok = key_in && (p.key_mask == nullptr || p.key_mask[(int64_t)b * S + s] != 0);
     const uint32_t pcol = hf ? 48 : 0;                  // where this half's packed P^T / dS^T columns go
 
-    auto load_stats = [&](int i, float4& v) {          // threads 0..63 of the group: column sid of iteration i
-      const int h = kvh * G + i / nq, qt = qt_first + i % nq;
+    auto load_stats = [&](int h, int qt, float4& v) {  // threads 0..63 of the group: column sid of tile (h, qt)
       const int t = qt * BQ + sid;
       v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t < T) {
@@ -263,17 +277,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
     float4 nxt;
     if (n > 0 && sid < BQ) {
-      load_stats(0, nxt);
+      load_stats(kvh * G, qt_first, nxt);
       stats[sid] = nxt;
     }
+    int cur_h = kvh * G, cur_qt = qt_first;             // (head, query tile) of iteration i, advanced without div/mod
     for (int i = 0; i < n; ++i) {
       const int st = i & 1;
-      const int qt = qt_first + i % nq;
+      const int qt = cur_qt;
       const int t0 = qt * BQ;
       const bool nc = need_c(qt);
-      if (i + 1 < n && sid < BQ) load_stats(i + 1, nxt);        // prefetch next iteration's row statistics
+      if (++cur_qt == n_qt) {
+        cur_qt = qt_first;
+        ++cur_h;
+      }
+      if (i + 1 < n && sid < BQ) load_stats(cur_h, cur_qt, nxt);   // prefetch next iteration's row statistics
+      const int srole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 2 : 3) : -1;
+      if (srole >= 0) stamp(srole, i, 0);
       if (!(p.debug_flags & 2048)) named_bar_sync(1, 256);      // stats[st] complete; stats[st^1] no longer read
+      if (srole >= 0) stamp(srole, i, 1);
       mbar_wait(&bars[S_FULL + st], (i >> 1) & 1, 310 + st);
+      if (srole >= 0) stamp(srole, i, 2);
       tc_fence_after();
       const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ;
       const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ;
@@ -288,6 +311,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tmem_ld32(t_s + 32 * hf, sv);
       if (nc) tmem_ld32(t_dp + 32 * hf, dpv);
       tc_wait_ld();
+      if (srole >= 0) stamp(srole, i, 3);
       uint32_t pk[16], dk_[16];
       const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFFFFFu);
       const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFFFFFu);
@@ -333,6 +357,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           dk_[c2] = pack_bf16(dsv[0], dsv[1]);
         }
       }
+      if (srole >= 0) stamp(srole, i, 4);
       if (nc) tmem_st16(t_s + pcol, pk);                        // P^T  (A operand of dV)
       tmem_st16(t_dp + pcol, dk_);                              // dS^T (A operand of dK)
       // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
@@ -348,6 +373,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (!(p.debug_flags & 1024)) fence_proxy_async();         // smem dS^T visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
+      if (srole >= 0) stamp(srole, i, 5);
     }
     // ---- epilogue: warps 2-5 write this key's dV row, warps 6-9 its dK row (x softmax scale) ----
     if (n > 0) {
@@ -389,7 +415,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int i = 0; i < n; ++i) {
       const int st = i & 1;
       const int h = kvh * G + i / nq, qt = qt_first + i % nq;
+      const bool dtr = (warp == 10 && lane == 0);
+      if (dtr) stamp(4, i, 0);
       mbar_wait(&bars[DQ_FULL + st], (i >> 1) & 1, 410 + st);
+      if (dtr) stamp(4, i, 1);
       tc_fence_after();
       float v0[32], v1[32];
       tmem_ld32(tmem_base + lane_off + TM_SDQ + st * BQ, v0);
@@ -397,6 +426,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
+      if (dtr) stamp(4, i, 2);
       if (p.debug_flags & 256) continue;
       const int rows = min(BQ, T - qt * BQ);
       float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
@@ -416,6 +446,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
       }
+      if (dtr) stamp(4, i, 3);
     }
     if (did == 0) bulk_wait0();
   }
@@ -434,6 +465,7 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   AttnParams pp = p;
   pp.dq_seed_mul = 1.f / p.scale;
   pp.dq_out_mul = p.scale;
+  pp.trace = debug_trace_capacity() >= 24 * 64 ? debug_trace_buffer() : nullptr;
   if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pp.debug_flags = atoi(e);   // bit 0: skip the dQ reduce (timing experiments only)
   if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
   CUtensorMap tq, tk, tv, tdo;
