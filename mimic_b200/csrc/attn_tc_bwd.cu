@@ -41,11 +41,11 @@ constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
 constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
 constexpr int STAGE_BYTES = 32 * HD * 4;   // fp32 dQ staging for 32 query rows, 16 KB (two bulk reduces per tile)
 constexpr int NQS = 3;                     // Q / dO TMA stages
-constexpr int THREADS = 448;                // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM quarter), warps 10-13 drain
+constexpr int THREADS = 704;                // warp 0 TMA, warp 1 MMA, warps 2-9 / 10-17 softmax groups 0 / 1, warps 18-21 drain
 constexpr float LOG2E = 1.4426950408889634f;
 
 constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + NQS * Q_TILE, OFF_DS = OFF_DO + NQS * Q_TILE,
-              OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 2 * BQ * 16,
+              OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 4 * BQ * 16,
               OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16;
 
 enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, N_BARS = 16 };
@@ -58,6 +58,9 @@ constexpr uint32_t IDESC_DQT = idesc_bf16(128, BQ, 1, 1);    // dQ^T      : A = 
 
 __device__ __forceinline__ uint32_t low_bits_b(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
+// DBG = true builds the instrumented twin (timeline stamps + MIMIC_DEBUG_FLAGS experiments); the production
+// instantiation carries none of it: the single MMA-issuing warp is instruction-fetch bound, every instruction counts.
+template <bool DBG>
 __global__ void __launch_bounds__(bw::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnParams p) {
@@ -74,17 +77,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* sDO = smem + OFF_DO;
   uint8_t* sDS = smem + OFF_DS;
   float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
-  float4* stats = reinterpret_cast<float4*>(smem + OFF_STATS);      // [2][64] (lse_c*log2e, Delta', dz, lse_full*log2e)
+  float4* stats = reinterpret_cast<float4*>(smem + OFF_STATS);      // [group][2][64] (-lse_c*log2e, Delta', -dz, -lse_full*log2e)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   // timeline trace (debug): role r writes record k of iteration i at trace[(i * 8 + r) * 8 + k]
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool tracing = DBG && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   auto stamp = [&](int role, int i, int k) {
-    if (tracing && i < 24) p.trace[(i * 8 + role) * 8 + k] = clock64();
+    if constexpr (DBG) {
+      if (tracing && i < 24) p.trace[(i * 8 + role) * 8 + k] = clock64();
+    }
   };
+  auto dbg = [&](int bit) { return DBG && (p.debug_flags & bit) != 0; };
   const int G = p.H / p.Hkv;
   const int T = p.T, S = p.S, off = p.S - p.T;
   const int s0 = kt * BN;
@@ -134,11 +140,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tma_load_4d(sK + KV_HALF, &tm_k, &bars[KV_FULL], 64, s0, kvh, b);
       tma_load_4d(sV, &tm_v, &bars[KV_FULL], 0, s0, kvh, b);
       tma_load_4d(sV + KV_HALF, &tm_v, &bars[KV_FULL], 64, s0, kvh, b);
+      int st = 0, ph = 1, h = kvh * G, qt = qt_first;   // ring stage, EMPTY-wait parity, (head, query tile) of iteration i
       for (int i = 0; i < n; ++i) {
-        const int st = i % NQS;
-        const int h = kvh * G + i / nq, qt = qt_first + i % nq;
         const bool nc = need_c(qt);
-        if (!(p.debug_flags & 8)) mbar_wait(&bars[QDO_EMPTY + st], ((i / NQS) & 1) ^ 1, 100 + st);
+        if (!dbg(8)) mbar_wait(&bars[QDO_EMPTY + st], ph, 100 + st);
         stamp(0, i, 0);
         mbar_expect_tx(&bars[QDO_FULL + st], nc ? 2 * Q_TILE : Q_TILE);
         tma_load_4d(sQ + st * Q_TILE, &tm_q, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
@@ -146,6 +151,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (nc) {
           tma_load_4d(sDO + st * Q_TILE, &tm_do, &bars[QDO_FULL + st], 0, qt * BQ, h, b);
           tma_load_4d(sDO + st * Q_TILE + Q_HALF, &tm_do, &bars[QDO_FULL + st], 64, qt * BQ, h, b);
+        }
+        if (DBG && tracing) {                            // debug: when did this stage's bytes land?
+          stamp(0, i, 1);
+          mbar_wait(&bars[QDO_FULL + st], ph ^ 1, 110 + st);
+          stamp(0, i, 2);
+        }
+        if (++qt == n_qt) {
+          qt = qt_first;
+          ++h;
+        }
+        if (++st == NQS) {
+          st = 0;
+          ph ^= 1;
         }
       }
     }
@@ -160,235 +178,270 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t q_mn0 = desc_lo(smem_u32(sQ), Q_HALF), do_mn0 = desc_lo(smem_u32(sDO), Q_HALF);
       const uint32_t ds_mn0 = desc_lo(smem_u32(sDS), 16);
       mbar_wait(&bars[KV_FULL], 0, 200);
-      auto issue_sdp = [&](int i) {
-        const int st = i & 1, qs = i % NQS;
-        const int qt = qt_first + i % nq;
-        const bool nc = need_c(qt);
-        if (!(p.debug_flags & 16)) mbar_wait(&bars[QDO_FULL + qs], (i / NQS) & 1, 210 + qs);
-        if (lane == 0) stamp(1, i, 0);
-        if (!(p.debug_flags & 2)) mbar_wait(&bars[DRAIN_DONE + st], ((i >> 1) & 1) ^ 1, 215 + st);   // dQ^T(i-2) left this TMEM buffer
-        if (lane == 0) stamp(1, i, 1);
+      // Tensor-pipe order per iteration i (st = i & 1):
+      //   dV(i)  dQ^T(i) | commit DQ_FULL  dK(i) | commit QDO_EMPTY  dP^T(i+2)  [DRAIN_DONE(i)]  S^T(i+2) | commit S_FULL
+      // dQ^T(i) lands in SdQ[st] over P^T(i) (dV(i) has read it: the pipe runs in issue order); the drain warps empty it
+      // while dK(i) and dP^T(i+2) run, so S^T(i+2) can be issued into the same columns without draining the pipe.
+      // All loop bookkeeping is incremental (no div/mod on the issue path).
+      auto issue_dp = [&](int st2, int qs2) {            // dP^T = V dO^T -> dP[st2]   (elected lane)
+        const uint32_t do_km = do_km0 + qs2 * (Q_TILE >> 4), d_p = tmem_base + TM_DP + st2 * BQ;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+          if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+          else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+        }
+      };
+      auto issue_s = [&](int st2, int qs2) {             // S^T = K Q^T -> SdQ[st2], then S_FULL   (elected lane)
+        const uint32_t q_km = q_km0 + qs2 * (Q_TILE >> 4), d_s = tmem_base + TM_SDQ + st2 * BQ;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+          if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
+          else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
+        }
+        tc_commit(&bars[S_FULL + st2]);
+      };
+      auto next_qt = [&](int qt) { return qt + 1 == n_qt ? qt_first : qt + 1; };
+      int qt_i = qt_first;                       // query tile of iteration i
+      int qt_2 = qt_first;                       // query tile of iteration i + 2
+      int qs = 0, qs2 = 0, qph2 = 0;             // Q/dO ring stage of iteration i; stage and phase of iteration i + 2
+      auto advance2 = [&]() {
+        qt_2 = next_qt(qt_2);
+        if (++qs2 == NQS) {
+          qs2 = 0;
+          qph2 ^= 1;
+        }
+      };
+      // prologue: S^T / dP^T of iterations 0 and 1 (their TMEM buffers are fresh)
+      for (int i2 = 0; i2 < 2 && i2 < n; ++i2) {
+        mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
+        if (lane == 0) stamp(1, i2, 0);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t q_km = q_km0 + qs * (Q_TILE >> 4), do_km = do_km0 + qs * (Q_TILE >> 4);
-          const uint32_t d_s = tmem_base + TM_SDQ + st * BQ, d_p = tmem_base + TM_DP + st * BQ;
-          if (!(p.debug_flags & 128))
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
-            if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
-            else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
-          }
-          if (nc && !(p.debug_flags & 128)) {
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {
-              const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
-              if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-              else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-            }
-          }
-          tc_commit(&bars[S_FULL + st]);
+          if (need_c(qt_2)) issue_dp(i2, qs2);
+          issue_s(i2, qs2);
         }
         __syncwarp();
-        if (lane == 0) stamp(1, i, 2);
-      };
+        if (lane == 0) stamp(1, i2, 2);
+        advance2();
+      }
       bool dv_started = false;
-      issue_sdp(0);
       for (int i = 0; i < n; ++i) {
-        const int st = i & 1, qs = i % NQS;
-        const int qt = qt_first + i % nq;
-        const bool nc = need_c(qt);
-        if (i + 1 < n) issue_sdp(i + 1);
+        const int st = i & 1;
+        const bool nc = need_c(qt_i);
+        const bool has2 = i + 2 < n;
+        const bool nc2 = has2 && need_c(qt_2);
+        if (lane == 0) stamp(5, i, 0);
+        // Q/dO of iteration i+2 landed a full iteration ago in steady state: taking this wait here keeps it off the
+        // stretch between the last dK MMA and the first dP^T MMA
+        if (has2) mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
+        if (lane == 0) stamp(1, i + 2, 0);
         mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
         if (lane == 0) stamp(1, i, 3);
         tc_fence_after();
+        if (lane == 0) stamp(5, i, 1);
         if (elect_one()) {
+          stamp(5, i, 2);
           const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
           const uint32_t ds_mn = ds_mn0 + st * (DS_TILE >> 4);
           const uint32_t a_p = tmem_base + TM_SDQ + st * BQ, a_ds = tmem_base + TM_DP + st * BQ;
-          if (nc && !(p.debug_flags & 64)) {
-            // dV += P^T dO_i : K = 16 queries per step (8 packed TMEM cols: queries 0-31 at cols 0.., 32-63 at cols 48..)
-            if (dv_started) {
-#pragma unroll
-              for (int k = 0; k < BQ / 16; ++k)
-                mma_ts_c<true>(tmem_base + TM_DV, a_p + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV);
-            } else {
-#pragma unroll
-              for (int k = 0; k < BQ / 16; ++k) {
-                if (k == 0) mma_ts_c<false>(tmem_base + TM_DV, a_p, desc64(HI, do_mn), IDESC_DKV);
-                else mma_ts_c<true>(tmem_base + TM_DV, a_p + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV);
-              }
-            }
-          }
-          // dK += dS^T Q_i
-          if (p.debug_flags & 64) {
-          } else if (i > 0) {
+          if (nc) {
+            // dV += P^T dO_i : K = 16 queries per step; step k's 8 packed TMEM cols sit at [16k, 16k+8) of the buffer
 #pragma unroll
             for (int k = 0; k < BQ / 16; ++k)
-              mma_ts_c<true>(tmem_base + TM_DK, a_ds + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV);
-          } else {
-#pragma unroll
-            for (int k = 0; k < BQ / 16; ++k) {
-              if (k == 0) mma_ts_c<false>(tmem_base + TM_DK, a_ds, desc64(HI, q_mn), IDESC_DKV);
-              else mma_ts_c<true>(tmem_base + TM_DK, a_ds + (k < 2 ? k * 8 : 48 + (k - 2) * 8), desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV);
-            }
+              mma_ts(tmem_base + TM_DV, a_p + 16 * k, desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || dv_started) ? 1u : 0u);
           }
-          // dQ^T = K^T dS^T : K = 16 keys per step
-          if (!(p.debug_flags & 32))
+          // dQ^T = K^T dS^T : K = 16 keys per step; overwrites P^T(i) in SdQ[st]
 #pragma unroll
           for (int k = 0; k < BN / 16; ++k) {
             if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
             else mma_ss_c<true>(a_p, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
           }
-          tc_commit(&bars[QDO_EMPTY + qs]);
           tc_commit(&bars[DQ_FULL + st]);
+          stamp(5, i, 3);
+          // dK += dS^T Q_i
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k)
+            mma_ts(tmem_base + TM_DK, a_ds + 16 * k, desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || i > 0) ? 1u : 0u);
+          tc_commit(&bars[QDO_EMPTY + qs]);
+          stamp(5, i, 4);
+          if (nc2) issue_dp(st, qs2);                      // dP^T(i+2) over dS^T(i): dK(i) has read it (pipe order)
+          stamp(5, i, 5);
         }
         __syncwarp();
         if (lane == 0) stamp(1, i, 4);
         if (nc) dv_started = true;
+        if (has2) {
+          if (!dbg(2)) mbar_wait(&bars[DRAIN_DONE + st], (i >> 1) & 1, 215 + st);   // dQ^T(i) left SdQ[st]
+          if (lane == 0) stamp(1, i + 2, 1);
+          tc_fence_after();
+          if (lane == 0) stamp(5, i, 6);
+          if (elect_one()) issue_s(st, qs2);
+          __syncwarp();
+          if (lane == 0) stamp(1, i + 2, 2);
+          advance2();
+        }
+        qt_i = next_qt(qt_i);
+        if (++qs == NQS) qs = 0;
       }
       if (elect_one()) tc_commit(&bars[DKV_FULL]);
       __syncwarp();
     }
-  } else if (warp < 10) {
-    // ===================== softmax warps: one key row x 32 query columns per thread =====================
-    // warps 2-5 take query columns 0-31 of the tile, warps 6-9 columns 32-63 (two warps per TMEM lane quarter)
+  } else if (warp < 18) {
+    // ===================== softmax warps: two ping-pong groups of 8 warps =====================
+    // Group g (warps 2+8g .. 9+8g) owns the iterations with i & 1 == g, i.e. TMEM / dS^T buffer st = g, so one group's
+    // TMEM loads overlap the other's exponentials and stores.  Inside a group, warp (quarter, hf) owns key rows of its
+    // TMEM lane quarter and query columns [32 hf, 32 hf + 32), processed as two 16-column passes (register budget).
+    const int g = (warp - 2) >> 3;
+    const int hf = ((warp - 2) >> 2) & 1;
     const int quarter = warp & 3;
-    const int hf = warp >= 6 ? 1 : 0;
     const int r = quarter * 32 + lane;
     const int s = s0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float scale2 = p.scale * LOG2E;
-    const int sid = threadIdx.x - 64;                   // 0..255 inside the softmax group
+    const int sid = threadIdx.x - 64 - 256 * g;         // 0..255 inside the group
     const bool key_in = s < S;
     const bool key_ok = key_in && (p.key_mask == nullptr || p.key_mask[(int64_t)b * S + s] != 0);
-    const uint32_t pcol = hf ? 48 : 0;                  // where this half's packed P^T / dS^T columns go
+    const int st = g;
 
-    auto load_stats = [&](int h, int qt, float4& v) {  // threads 0..63 of the group: column sid of tile (h, qt)
-      const int t = qt * BQ + sid;
-      v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < T) {
-        const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
-        v.x = -p.lse_c[ridx] * LOG2E;                   // negated: exp2(fma(s, scale2, -lse))
-        v.y = p.delta_ws[ridx];
-        v.z = -p.dz_ws[ridx];
-        v.w = p.active ? -p.lse_full[ridx] * LOG2E : 0.f;
+    // Row statistics of the group's NEXT iteration are fetched as raw values at the top of an iteration and only
+    // touched (negate / scale) when they are stored to shared memory at its end, so the global-load latency never sits
+    // on the softmax critical path.  Threads 0..63 of the group own column sid of the tile.
+    auto load_stats = [&](int h, int qt, float4& v) {
+      const int t = min(qt * BQ + sid, T - 1);          // clamped: no branch around the loads
+      const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
+      v.x = p.lse_c[ridx];
+      v.y = p.delta_ws[ridx];
+      v.z = p.dz_ws[ridx];
+      v.w = p.active ? p.lse_full[ridx] : 0.f;
+    };
+    auto finish_stats = [&](int qt, float4 v) {         // (-lse_c*log2e, Delta', -dz, -lse_full*log2e); rows >= T are zero
+      const bool in = qt * BQ + sid < T;
+      return in ? make_float4(-v.x * LOG2E, v.y, -v.z, -v.w * LOG2E) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int cur_h = kvh * G, cur_qt = qt_first;             // (head, query tile) of the group's current iteration
+    auto advance = [&](int& h, int& qt) {
+      if (++qt == n_qt) {
+        qt = qt_first;
+        ++h;
       }
     };
-    float4 nxt;
-    if (n > 0 && sid < BQ) {
-      load_stats(kvh * G, qt_first, nxt);
-      stats[sid] = nxt;
+    if (g == 1) advance(cur_h, cur_qt);
+    float4* gstats = stats + g * 2 * BQ;                // [2][64] per group
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < n && sid < BQ) {
+      load_stats(cur_h, cur_qt, nxt);
+      gstats[sid] = finish_stats(cur_qt, nxt);
     }
-    int cur_h = kvh * G, cur_qt = qt_first;             // (head, query tile) of iteration i, advanced without div/mod
-    for (int i = 0; i < n; ++i) {
-      const int st = i & 1;
+    int sb = 0;                                          // statistics buffer of the current iteration
+    for (int i = g; i < n; i += 2) {
       const int qt = cur_qt;
       const int t0 = qt * BQ;
       const bool nc = need_c(qt);
-      if (++cur_qt == n_qt) {
-        cur_qt = qt_first;
-        ++cur_h;
-      }
-      if (i + 1 < n && sid < BQ) load_stats(cur_h, cur_qt, nxt);   // prefetch next iteration's row statistics
-      const int srole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 2 : 3) : -1;
+      advance(cur_h, cur_qt);
+      advance(cur_h, cur_qt);                            // -> iteration i + 2
+      if (i + 2 < n && sid < BQ) load_stats(cur_h, cur_qt, nxt);
+      const int srole = (lane == 0 && (warp == 2 || warp == 10)) ? 2 + g : -1;
       if (srole >= 0) stamp(srole, i, 0);
-      if (!(p.debug_flags & 2048)) named_bar_sync(1, 256);      // stats[st] complete; stats[st^1] no longer read
+      named_bar_sync(1 + g, 256);                        // gstats[sb] complete; gstats[sb^1] no longer read
       if (srole >= 0) stamp(srole, i, 1);
       mbar_wait(&bars[S_FULL + st], (i >> 1) & 1, 310 + st);
       if (srole >= 0) stamp(srole, i, 2);
       tc_fence_after();
-      const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ;
-      const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ;
       uint8_t* ds_row = sDS + st * DS_TILE + r * 128;
-      const float4* stt = stats + st * BQ + 32 * hf;
-      // visibility of queries t0+32*hf+c (c = 0..31) for key s: visible iff s <= t + off
-      const uint32_t trow = low_bits_b(T - t0 - 32 * hf);
-      const uint32_t cz = p.causal ? ~low_bits_b(s - off - t0 - 32 * hf) : 0xFFFFFFFFu;
-      const uint32_t vw = key_ok ? (trow & cz) : 0u;
-      const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
-      float sv[32], dpv[32];
-      tmem_ld32(t_s + 32 * hf, sv);
-      if (nc) tmem_ld32(t_dp + 32 * hf, dpv);
-      tc_wait_ld();
-      if (srole >= 0) stamp(srole, i, 3);
-      uint32_t pk[16], dk_[16];
-      const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFFFFFu);
-      const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFFFFFu);
-      if (p.debug_flags & 4) {
 #pragma unroll
-        for (int c2 = 0; c2 < 16; ++c2) { pk[c2] = __float_as_uint(sv[c2]); dk_[c2] = __float_as_uint(sv[c2 + 16]); }
-      } else if (all_v && nc) {
-        // interior causal tile: every entry visible.  dS (unscaled) = P (dP - Delta'); scale is applied to dK / dQ later
+      for (int pass = 0; pass < 2; ++pass) {
+        const int cq = 2 * hf + pass;                    // 16-column group of the 64-wide tile
+        const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ + 16 * cq;
+        const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ + 16 * cq;
+        const float4* stt = gstats + sb * BQ + 16 * cq;
+        // visibility of queries t0+16*cq+c (c = 0..15) for key s: visible iff s <= t + off
+        const uint32_t trow = low_bits_b(T - t0 - 16 * cq) & 0xFFFFu;
+        const uint32_t cz = (p.causal ? ~low_bits_b(s - off - t0 - 16 * cq) : 0xFFFFFFFFu) & 0xFFFFu;
+        const uint32_t vw = key_ok ? (trow & cz) : 0u;
+        const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
+        float sv[16], dpv[16];
+        tmem_ld16(t_s, sv);
+        if (nc) tmem_ld16(t_dp, dpv);
+        tc_wait_ld();
+        if (srole >= 0 && pass == 0) stamp(srole, i, 3);
+        uint32_t pk[8], dk_[8];
+        const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFu);
+        const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFu);
+        if (all_v && nc) {
+          // interior causal tile: every entry visible.  dS (unscaled) = P (dP - Delta'); scale is applied to dK / dQ later
 #pragma unroll
-        for (int c2 = 0; c2 < 16; ++c2) {
-          const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
-          const float p0 = ex2(fmaf(sv[2 * c2], scale2, a.x)), p1 = ex2(fmaf(sv[2 * c2 + 1], scale2, bq.x));
-          pk[c2] = pack_bf16(p0, p1);
-          dk_[c2] = pack_bf16(p0 * (dpv[2 * c2] - a.y), p1 * (dpv[2 * c2 + 1] - bq.y));
-        }
-      } else if (all_x) {
-        // tile above the diagonal (shift term only): dS = -dz exp2(s - lse_full)
-#pragma unroll
-        for (int c2 = 0; c2 < 16; ++c2) {
-          const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
-          pk[c2] = 0u;
-          dk_[c2] = pack_bf16(a.z * ex2(fmaf(sv[2 * c2], scale2, a.w)), bq.z * ex2(fmaf(sv[2 * c2 + 1], scale2, bq.w)));
-        }
-      } else {
-#pragma unroll
-        for (int c2 = 0; c2 < 16; ++c2) {
-          float pv[2], dsv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 2 * c2 + e;
-            const float4 stc = stt[c];
-            float pe = 0.f, de = 0.f;
-            if ((vw >> c) & 1u) {
-              pe = ex2(fmaf(sv[c], scale2, stc.x));
-              de = pe * ((nc ? dpv[c] : 0.f) - stc.y);
-            } else if ((xw >> c) & 1u) {
-              de = stc.z * ex2(fmaf(sv[c], scale2, stc.w));
-            }
-            pv[e] = pe;
-            dsv[e] = de;
+          for (int c2 = 0; c2 < 8; ++c2) {
+            const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
+            const float p0 = ex2(fmaf(sv[2 * c2], scale2, a.x)), p1 = ex2(fmaf(sv[2 * c2 + 1], scale2, bq.x));
+            pk[c2] = pack_bf16(p0, p1);
+            dk_[c2] = pack_bf16(p0 * (dpv[2 * c2] - a.y), p1 * (dpv[2 * c2 + 1] - bq.y));
           }
-          pk[c2] = pack_bf16(pv[0], pv[1]);
-          dk_[c2] = pack_bf16(dsv[0], dsv[1]);
+        } else if (all_x) {
+          // tile above the diagonal (shift term only): dS = -dz exp2(s - lse_full)
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2) {
+            const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
+            pk[c2] = 0u;
+            dk_[c2] = pack_bf16(a.z * ex2(fmaf(sv[2 * c2], scale2, a.w)), bq.z * ex2(fmaf(sv[2 * c2 + 1], scale2, bq.w)));
+          }
+        } else {
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2) {
+            float pv[2], dsv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 2 * c2 + e;
+              const float4 stc = stt[c];
+              float pe = 0.f, de = 0.f;
+              if ((vw >> c) & 1u) {
+                pe = ex2(fmaf(sv[c], scale2, stc.x));
+                de = pe * ((nc ? dpv[c] : 0.f) - stc.y);
+              } else if ((xw >> c) & 1u) {
+                de = stc.z * ex2(fmaf(sv[c], scale2, stc.w));
+              }
+              pv[e] = pe;
+              dsv[e] = de;
+            }
+            pk[c2] = pack_bf16(pv[0], pv[1]);
+            dk_[c2] = pack_bf16(dsv[0], dsv[1]);
+          }
+        }
+        if (srole >= 0 && pass == 1) stamp(srole, i, 4);
+        if (nc) tmem_st8(t_s, pk);                              // P^T  (A operand of dV): packed cols [16cq, 16cq+8)
+        tmem_st8(t_dp, dk_);                                    // dS^T (A operand of dK)
+        // dS^T row to smem: 16 queries = 32 B = two 16-byte chunks, 128B-swizzled by key row
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int chunk = cq * 2 + ch;
+          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(dk_[4 * ch], dk_[4 * ch + 1], dk_[4 * ch + 2], dk_[4 * ch + 3]);
         }
       }
-      if (srole >= 0) stamp(srole, i, 4);
-      if (nc) tmem_st16(t_s + pcol, pk);                        // P^T  (A operand of dV)
-      tmem_st16(t_dp + pcol, dk_);                              // dS^T (A operand of dK)
-      // dS^T row to smem: 32 queries = 64 B = four 16-byte chunks, 128B-swizzled by key row
-      if (!(p.debug_flags & 512))
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int chunk = hf * 4 + ch;
-        *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
-            make_uint4(dk_[4 * ch], dk_[4 * ch + 1], dk_[4 * ch + 2], dk_[4 * ch + 3]);
-      }
-      if (i + 1 < n && sid < BQ) stats[(st ^ 1) * BQ + sid] = nxt;
+      if (i + 2 < n && sid < BQ) gstats[(sb ^ 1) * BQ + sid] = finish_stats(cur_qt, nxt);
+      sb ^= 1;
       tc_wait_st();
-      if (!(p.debug_flags & 1024)) fence_proxy_async();         // smem dS^T visible to the tensor-core (async) proxy
+      fence_proxy_async();                                      // smem dS^T visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
       if (srole >= 0) stamp(srole, i, 5);
     }
-    // ---- epilogue: warps 2-5 write this key's dV row, warps 6-9 its dK row (x softmax scale) ----
+    // ---- epilogue: group 0 writes this key's dV row, group 1 its dK row (x scale); hf picks the 64-column half ----
     if (n > 0) {
       mbar_wait(&bars[DKV_FULL], 0, 330);
       tc_fence_after();
     }
     {
-      const int which = hf;                              // 0: dV, 1: dK
+      const int which = g;                               // 0: dV, 1: dK
+      const int half = hf;                               // 64-column half of the row
       const float mul = which ? p.scale : 1.f;
-      __nv_bfloat16* dst0 = reinterpret_cast<__nv_bfloat16*>(which ? p.dk : p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD;
+      __nv_bfloat16* dst0 = reinterpret_cast<__nv_bfloat16*>(which ? p.dk : p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD + 64 * half;
 #pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
+      for (int i4 = 0; i4 < 2; ++i4) {
         float o[32];
         if (n > 0) {
-          tmem_ld32(tmem_base + lane_off + (which ? TM_DK : TM_DV) + 32 * i4, o);
+          tmem_ld32(tmem_base + lane_off + (which ? TM_DK : TM_DV) + 64 * half + 32 * i4, o);
           tc_wait_ld();
         } else {
 #pragma unroll
@@ -411,11 +464,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int quarter = warp & 3;
     const int c = quarter * 32 + lane;                  // head-dim index owned by this thread
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int did = threadIdx.x - 320;                  // 0..127
+    const int did = threadIdx.x - 576;                  // 0..127
+    int h = kvh * G, qt = qt_first - 1;
     for (int i = 0; i < n; ++i) {
       const int st = i & 1;
-      const int h = kvh * G + i / nq, qt = qt_first + i % nq;
-      const bool dtr = (warp == 10 && lane == 0);
+      if (++qt == n_qt) {
+        qt = qt_first;
+        ++h;
+      }
+      const bool dtr = (warp == 18 && lane == 0);
       if (dtr) stamp(4, i, 0);
       mbar_wait(&bars[DQ_FULL + st], (i >> 1) & 1, 410 + st);
       if (dtr) stamp(4, i, 1);
@@ -427,18 +484,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
       if (dtr) stamp(4, i, 2);
-      if (p.debug_flags & 256) continue;
+      if (dbg(256)) continue;
       const int rows = min(BQ, T - qt * BQ);
       float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         if (did == 0) bulk_wait_read0();                // previous bulk reduce finished reading the staging tile
-        named_bar_sync(2, 128);
+        named_bar_sync(4, 128);
 #pragma unroll
         for (int t = 0; t < 32; ++t) stage[t * HD + c] = half ? v1[t] : v0[t];
         fence_proxy_async();
         named_bar_sync(3, 128);
-        if (did == 0 && !(p.debug_flags & 1)) {
+        if (did == 0 && !dbg(1)) {
           const int r0 = half * 32, nr = min(32, rows - r0);
           if (nr > 0) {
             bulk_reduce_add_f32(gdst + (int64_t)r0 * HD, stage, (uint32_t)nr * HD * 4);
@@ -475,11 +532,13 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   if ((rc = make_map(&tdo, p.d_out, p.B, p.H, p.T, p.go_sb, p.go_sh, p.go_st, BQ))) return rc;
   static bool configured = false;
   if (!configured) {
-    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
-  attn_bwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
+  if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
+  else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
   return simt::convert_dq_bf16(pp, st);
 }

@@ -153,6 +153,9 @@ if __name__ == "__main__":
         bperf(4, 32, 32, 4096, False)
         bperf(4, 32, 32, 4096, True)
         bperf(2, 32, 32, 8192, True)
+    if which == "bperf1":
+        bperf(4, 32, 32, 4096, False)
+        bperf(4, 32, 32, 4096, True)
     if which in ("all", "perf"):
         perf(2, 32, 8, 3200, False)
         perf(2, 32, 8, 3200, True)
