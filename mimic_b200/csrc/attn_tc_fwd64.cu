@@ -84,9 +84,21 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&bars[PV_DONE], 1);
       mbar_init(&bars[O_FULL], 1);
       fence_barrier_init();
-      prefetch_tmap(&tm_q);
-      prefetch_tmap(&tm_k);
-      prefetch_tmap(&tm_v);
+      // First ring fill goes out before the CTA-wide sync: the Q / K / V round trips (~1 us) run under the TMEM
+      // allocation and the key-bit table build instead of after them.  (Consumers only touch the barriers after the sync.)
+      mbar_expect_tx(&bars[Q_FULL], Q_TILE);
+      tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, t0, h, b);
+      tma_load_4d(sQ + Q_HALF, &tm_q, &bars[Q_FULL], 64, t0, h, b);
+      for (int j = 0; j < NKV && j < n; ++j) {
+        mbar_expect_tx(&bars[K_FULL + j], KV_TILE);
+        tma_load_4d(sK + j * KV_TILE, &tm_k, &bars[K_FULL + j], 0, j * BN, kvh, b);
+        tma_load_4d(sK + j * KV_TILE + KV_HALF, &tm_k, &bars[K_FULL + j], 64, j * BN, kvh, b);
+        if (j <= jd) {
+          mbar_expect_tx(&bars[V_FULL + j], KV_TILE);
+          tma_load_4d(sV + j * KV_TILE, &tm_v, &bars[V_FULL + j], 0, j * BN, kvh, b);
+          tma_load_4d(sV + j * KV_TILE + KV_HALF, &tm_v, &bars[V_FULL + j], 64, j * BN, kvh, b);
+        }
+      }
     }
     __syncwarp();
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -113,10 +125,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(&bars[Q_FULL], Q_TILE);
-      tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, t0, h, b);
-      tma_load_4d(sQ + Q_HALF, &tm_q, &bars[Q_FULL], 64, t0, h, b);
-      for (int j = 0; j < n; ++j) {
+      for (int j = NKV; j < n; ++j) {                    // tiles 0 .. NKV-1 were issued in the prologue
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 100 + st);
@@ -356,25 +365,26 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_sb + (int64_t)t * p.o_st + (int64_t)h * p.o_sh;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float o[32];
+    for (int i2 = 0; i2 < 2; ++i2) {                     // two 64-column halves: both TMEM loads in flight before the wait
+      float o[64];
       if (jd >= 0) {
-        tmem_ld32(tmem_O + lane_off + 32 * i, o);
+        tmem_ld32(tmem_O + lane_off + 64 * i2, *reinterpret_cast<float(*)[32]>(o));
+        tmem_ld32(tmem_O + lane_off + 64 * i2 + 32, *reinterpret_cast<float(*)[32]>(o + 32));
         tc_wait_ld();
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) o[c] = 0.f;
+        for (int c = 0; c < 64; ++c) o[c] = 0.f;
       }
       if (row_ok) {
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
+        for (int c8 = 0; c8 < 8; ++c8) {
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int c = 32 * i + 8 * c8 + e;
+            const int c = 64 * i2 + 8 * c8 + e;
             f[e] = o[8 * c8 + e] * inv + (p.active ? mu * shift_s[c] : 0.f);
           }
-          store8(orow + 32 * i + 8 * c8, f);
+          store8(orow + 64 * i2 + 8 * c8, f);
         }
       }
     }
