@@ -150,6 +150,35 @@ MIMIC_API int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, in
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Layer-wise alignment loss, Strategy.LAYER_WISE_COS_SIM (src/shift_model.py:152-160), forward + backward in
+ * one pass.  Same arguments and workspace as mimic_mse_fwd_bwd (mimic_mse_workspace), D <= 8192:
+ *   loss = mean_i mean_l (1 - mean_t cos(H_i[l,t], H'_i[l,t])) = sum_{l,n} row_w[n] * (1 - cos_ln)
+ * with row_w[n] = 1 / (n_samples * L * Nq_{sample(n)}) supplied by the caller; cos as F.cosine_similarity
+ * (each norm clamped at 1e-8).  dH = -grad_scale * row_w * (h'/(|h||h'|) - cos * h/|h|^2), zeros on unselected rows.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_cos_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype,
+                      const void* hp, int32_t hp_dtype,
+                      const int32_t* row_to_compact, const float* row_w,
+                      void* const* dh_ptrs, float grad_scale,
+                      int32_t L, int32_t rows, int32_t N, int32_t D,
+                      float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Logits KL divergence, Strategy.LOGITS_KL_DIV, forward + backward in one launch.  Replaces
+ * ShiftModel.calculate_logits_kl_loss (src/shift_model.py:181-191): F.kl_div(log_softmax(shift_logits[mask_q]),
+ * softmax(prefix_logits[mask_p]), reduction="batchmean") and its autograd, without the two masked copies.
+ *   z [R, V] query-pass logits (row stride z_row_stride); y [*, V] context-pass logits (y_row_stride);
+ *   y_row int32 [R]: row of y paired with row i of z, or < 0 when row i is not selected.
+ *   dz [R, V] with the strides of z (may alias z); NULL = forward only:
+ *            dz = grad_scale / n_rows * (softmax(z) - softmax(y)), 0 on unselected rows.
+ *   loss fp32 [1] = sum of row KLs / n_rows (0 when none); n_rows int32 [1].
+ *   workspace: mimic_ce_workspace(R) bytes, ZERO on first use.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_kl_fwd_bwd(const void* z, int64_t z_row_stride, const void* y, int64_t y_row_stride, int32_t dtype,
+                     const int32_t* y_row, void* dz, float grad_scale, int32_t R, int32_t V,
+                     float* loss, int32_t* n_rows, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * On-device optimizer step for the flat fp32 shift-parameter buffer: global-norm clip
  * (train.yaml grad_clip_val) + AdamW with per-element weight decay (the reference's two groups,
  * src/shift_model.py:306-372: names containing "bias" get 0).  Replaces DeepSpeedCPUAdam's host

@@ -42,6 +42,12 @@ EXPORTS = {
     "mimic_mse_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mimic_cos_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mimic_kl_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
     "mimic_ce_workspace": (C.c_size_t, [C.c_int32]),
     "mimic_ce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -50,15 +56,26 @@ EXPORTS = {
 }
 
 
-def _load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build   # needs nvcc; raises when it is missing
-        _build.build()
-    lib = C.CDLL(LIB_PATH)
+def _bind(path: str) -> C.CDLL:
+    lib = C.CDLL(path)
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    return lib
+
+
+def _load() -> C.CDLL:
+    import fcntl
+    from . import build as _build
+    try:
+        with open(LIB_PATH + ".lock", "w") as lock:      # ranks of one job import at the same time: one builds, the rest wait
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            _build.build()            # no-op when the library is newer than csrc/ and include/; needs nvcc otherwise
+    except RuntimeError:
+        if not os.path.exists(LIB_PATH):
+            raise                     # no library and no way to build it: fail loudly, there is no fallback path
+    lib = _bind(LIB_PATH)             # AttributeError when a prebuilt library is older than the header
     if lib.mimic_abi_version() != 1:
         raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 1; rebuild (python -m mimic_b200.build --force)")
     return lib

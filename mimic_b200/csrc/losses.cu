@@ -395,6 +395,262 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const T* __restrict__ l
 }
 
 // ---------------------------------------------------------------------------------------------
+// Layer-wise cosine-similarity alignment (Strategy.LAYER_WISE_COS_SIM, src/shift_model.py:152-160), forward +
+// backward in one launch.  One CTA per (layer, row) item keeps the row of H and H' in registers between the
+// reduction (h.h', |h|^2, |h'|^2) and the gradient, so HBM is read once:  3 * N * sizeof(T) algorithmic bytes, as M.
+//   loss = sum_{l,n} row_w[n] * (1 - cos_ln),  cos = h.h' / (max(|h|, eps) * max(|h'|, eps))   (F.cosine_similarity, eps 1e-8)
+//   dH   = -grad_scale * row_w * ( h' / (|h||h'|) - cos * h / |h|^2 )
+template <typename T, int MAXU>
+__global__ void __launch_bounds__(256) cos_fwd_bwd_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
+                                                          const T* __restrict__ hp,
+                                                          const int32_t* __restrict__ row_to_compact,
+                                                          const float* __restrict__ row_w,
+                                                          void* const* __restrict__ dh_ptrs, float grad_scale, int L,
+                                                          int rows, int N, int D, float* __restrict__ partial,
+                                                          unsigned int* __restrict__ counter, float* __restrict__ loss) {
+  __shared__ float red[3][32];
+  __shared__ float bc[3];
+  __shared__ bool is_last;
+  const int chunks = D / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t items = (int64_t)L * rows;
+  float acc = 0.f;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int l = (int)(it / rows), r = (int)(it % rows);
+    const int c = row_to_compact[r];
+    T* dh = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) + (int64_t)r * D : nullptr;
+    if (c < 0) {
+      if (dh) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) Chunk<T>::store(dh + ch * 8, z);
+      }
+      continue;
+    }
+    const T* h = reinterpret_cast<const T*>(h_ptrs[l]) + (int64_t)r * h_row_stride;
+    const T* t = hp + ((int64_t)l * N + c) * D;
+    float a[MAXU][8], b[MAXU][8];
+    float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int ch = threadIdx.x + u * blockDim.x;
+      if (ch < chunks) {
+        Chunk<T>::load(h + ch * 8, a[u]);
+        Chunk<T>::load(t + ch * 8, b[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int ch = threadIdx.x + u * blockDim.x;
+      if (ch < chunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dot = fmaf(a[u][e], b[u][e], dot);
+          na = fmaf(a[u][e], a[u][e], na);
+          nb = fmaf(b[u][e], b[u][e], nb);
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    na = warp_sum(na);
+    nb = warp_sum(nb);
+    __syncthreads();                                   // previous item's bc[] reads are done
+    if (lane == 0) {
+      red[0][warp] = dot;
+      red[1][warp] = na;
+      red[2][warp] = nb;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float v0 = lane < nw ? red[0][lane] : 0.f, v1 = lane < nw ? red[1][lane] : 0.f, v2 = lane < nw ? red[2][lane] : 0.f;
+      v0 = warp_sum(v0);
+      v1 = warp_sum(v1);
+      v2 = warp_sum(v2);
+      if (lane == 0) {
+        bc[0] = v0;
+        bc[1] = v1;
+        bc[2] = v2;
+      }
+    }
+    __syncthreads();
+    const float ha = fmaxf(sqrtf(bc[1]), 1e-8f), hb = fmaxf(sqrtf(bc[2]), 1e-8f);
+    const float inv = 1.f / (ha * hb);
+    const float cs = bc[0] * inv;
+    const float w = row_w[c];
+    if (threadIdx.x == 0) acc += w * (1.f - cs);
+    if (dh) {
+      const float gw = -grad_scale * w;
+      const float k1 = gw * inv, k2 = gw * cs / (ha * ha);
+#pragma unroll
+      for (int u = 0; u < MAXU; ++u) {
+        const int ch = threadIdx.x + u * blockDim.x;
+        if (ch < chunks) {
+          float g[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = k1 * b[u][e] - k2 * a[u][e];
+          Chunk<T>::store(dh + ch * 8, g);
+        }
+      }
+    }
+  }
+  acc = block_sum(acc, red[0]);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
+    tot = block_sum(tot, red[0]);
+    if (threadIdx.x == 0) {
+      loss[0] = tot;
+      *counter = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Logits KL divergence (Strategy.LOGITS_KL_DIV, src/shift_model.py:181-191), forward + backward in one launch:
+//   loss = (1/R) sum_r KL( softmax(y_r) || softmax(z_r) ),   dz = grad_scale / R * (softmax(z) - softmax(y))
+// z = query-pass ("shift") logits row i, y = context-pass ("prefix") logits row y_row[i]; y_row[i] < 0 = row not selected
+// (gradient row zeroed).  Rows of the two tensors start at unrelated alignments (V is odd for the real vocabularies), so the
+// loads are element-wise and warp-coalesced rather than 16-byte chunks: every sector is still fully used.  Pass 1 keeps
+// online (max, sum) for both rows plus A = sum e^{y-m}(y - z);  KL_r = A / S_y - lse_y + lse_z.  Pass 2 re-reads both rows
+// (L2) and writes the gradient:  3 * R * V * sizeof(T) algorithmic bytes.
+struct KlAcc {
+  float mz, sz, my, sy, ay;
+};
+__device__ __forceinline__ void kl_add(KlAcc& k, float z, float y) {
+  if (z > k.mz) {
+    k.sz *= __expf(k.mz - z);
+    k.mz = z;
+  }
+  k.sz += __expf(z - k.mz);
+  if (y > k.my) {
+    const float f = __expf(k.my - y);
+    k.sy *= f;
+    k.ay *= f;
+    k.my = y;
+  }
+  const float e = __expf(y - k.my);
+  k.sy += e;
+  k.ay = fmaf(e, y - z, k.ay);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) kl_fwd_bwd_kernel(const T* __restrict__ zl, int64_t z_stride, const T* __restrict__ yl,
+                                                         int64_t y_stride, const int32_t* __restrict__ y_row, T* dz,
+                                                         float grad_scale, int R, int V, int32_t* __restrict__ n_rows,
+                                                         float* __restrict__ loss, float* __restrict__ row_loss,
+                                                         unsigned int* __restrict__ counter) {
+  __shared__ float red[32];
+  __shared__ float bc[5];
+  __shared__ bool is_last;
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += y_row[i] >= 0 ? 1.f : 0.f;
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) bc[0] = cnt;
+  __syncthreads();
+  const float n_sel = bc[0];
+  __syncthreads();
+  const float inv_n = n_sel > 0.f ? 1.f / n_sel : 0.f;
+  constexpr int U = 8;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const T* z = zl + (int64_t)r * z_stride;
+    T* d = dz ? dz + (int64_t)r * z_stride : nullptr;
+    const int yr = y_row[r];
+    if (yr < 0) {
+      if (threadIdx.x == 0) row_loss[r] = 0.f;
+      if (d)
+        for (int i = threadIdx.x; i < V; i += blockDim.x) d[i] = from_f32<T>(0.f);
+      continue;
+    }
+    const T* y = yl + (int64_t)yr * y_stride;
+    KlAcc k = {-INFINITY, 0.f, -INFINITY, 0.f, 0.f};
+    for (int i0 = threadIdx.x; i0 < V; i0 += blockDim.x * U) {
+      float fz[U], fy[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < V) {
+          fz[u] = to_f32(z[i]);
+          fy[u] = to_f32(y[i]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * blockDim.x < V) kl_add(k, fz[u], fy[u]);
+    }
+    // block combine: maxima first, then the rescaled sums
+    float gz = k.mz, gy = k.my;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gz = fmaxf(gz, __shfl_xor_sync(0xffffffffu, gz, o));
+      gy = fmaxf(gy, __shfl_xor_sync(0xffffffffu, gy, o));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gz;
+    __syncthreads();
+    gz = red[0];
+    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) gz = fmaxf(gz, red[wi]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gy;
+    __syncthreads();
+    gy = red[0];
+    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) gy = fmaxf(gy, red[wi]);
+    const float fzs = (k.mz == -INFINITY) ? 0.f : __expf(k.mz - gz), fys = (k.my == -INFINITY) ? 0.f : __expf(k.my - gy);
+    const float sz = block_sum(k.sz * fzs, red);
+    if (threadIdx.x == 0) bc[1] = sz;
+    const float sy = block_sum(k.sy * fys, red);
+    if (threadIdx.x == 0) bc[2] = sy;
+    const float ay = block_sum(k.ay * fys, red);
+    if (threadIdx.x == 0) bc[3] = ay;
+    __syncthreads();
+    const float Sz = bc[1], Sy = bc[2], Ay = bc[3];
+    const float lse_z = gz + __logf(Sz), lse_y = gy + __logf(Sy);
+    if (threadIdx.x == 0) row_loss[r] = Ay / Sy - lse_y + lse_z;
+    if (d) {
+      const float gs = grad_scale * inv_n;
+      for (int i0 = threadIdx.x; i0 < V; i0 += blockDim.x * U) {
+        float fz[U], fy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < V) {
+            fz[u] = to_f32(z[i]);
+            fy[u] = to_f32(y[i]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < V) d[i] = from_f32<T>(gs * (__expf(fz[u] - lse_z) - __expf(fy[u] - lse_y)));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      loss[0] = tot * inv_n;
+      n_rows[0] = (int32_t)(n_sel + 0.5f);
+      *counter = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // clip + AdamW on the flat fp32 parameter buffer
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ grad, int64_t n, float grad_mul, float* __restrict__ sumsq) {
   __shared__ float red[32];
@@ -525,6 +781,65 @@ extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, i
     return MIMIC_ERR_UNSUPPORTED;
   }
   MIMIC_LAUNCH_OK("ce_fwd_bwd_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" int mimic_cos_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride, int32_t h_dtype, const void* hp,
+                                 int32_t hp_dtype, const int32_t* row_to_compact, const float* row_w,
+                                 void* const* dh_ptrs, float grad_scale, int32_t L, int32_t rows, int32_t N,
+                                 int32_t D, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  MIMIC_CHECK_ARG(h_ptrs && hp && row_to_compact && row_w && loss && workspace, "NULL argument");
+  MIMIC_CHECK_ARG(L > 0 && rows > 0 && N >= 0 && D > 0 && D % 8 == 0 && h_row_stride % 8 == 0, "bad shape");
+  MIMIC_CHECK_ARG(D <= 256 * 8 * 4, "cos: D up to 8192 (one row of H and H' lives in the CTA's registers), got %d", D);
+  MIMIC_CHECK_ARG(h_dtype == hp_dtype, "H and H' must have the same storage type (got %d, %d)", h_dtype, hp_dtype);
+  MIMIC_CHECK_ARG(workspace_bytes >= mimic_mse_workspace(L, rows, D), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = mse_grid(L, rows);
+  float* partial = static_cast<float*>(workspace) + 4;
+  unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
+  const bool small = D <= 256 * 8 * 2;
+  if (h_dtype == MIMIC_BF16 && small)
+    cos_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_BF16)
+    cos_fwd_bwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_F32 && small)
+    cos_fwd_bwd_kernel<float, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w, dh_ptrs,
+                                                       grad_scale, L, rows, N, D, partial, counter, loss);
+  else if (h_dtype == MIMIC_F32)
+    cos_fwd_bwd_kernel<float, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w, dh_ptrs,
+                                                       grad_scale, L, rows, N, D, partial, counter, loss);
+  else {
+    set_error("cos: unsupported dtype %d", h_dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("cos_fwd_bwd_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" int mimic_kl_fwd_bwd(const void* z, int64_t z_row_stride, const void* y, int64_t y_row_stride, int32_t dtype,
+                                const int32_t* y_row, void* dz, float grad_scale, int32_t R, int32_t V, float* loss,
+                                int32_t* n_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  MIMIC_CHECK_ARG(z && y && y_row && loss && n_rows && workspace, "NULL argument");
+  MIMIC_CHECK_ARG(R > 0 && V > 0 && z_row_stride >= V && y_row_stride >= V, "bad shape");
+  MIMIC_CHECK_ARG(workspace_bytes >= mimic_ce_workspace(R), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
+  float* row_loss = static_cast<float*>(workspace) + 4;
+  const int grid = R < num_sms() * 4 ? R : num_sms() * 4;
+  if (dtype == MIMIC_BF16)
+    kl_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)z, z_row_stride, (const __nv_bfloat16*)y,
+                                                           y_row_stride, y_row, (__nv_bfloat16*)dz, grad_scale, R, V, n_rows,
+                                                           loss, row_loss, counter);
+  else if (dtype == MIMIC_F32)
+    kl_fwd_bwd_kernel<float><<<grid, 512, 0, st>>>((const float*)z, z_row_stride, (const float*)y, y_row_stride, y_row,
+                                                   (float*)dz, grad_scale, R, V, n_rows, loss, row_loss, counter);
+  else {
+    set_error("kl: unsupported dtype %d", dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("kl_fwd_bwd_kernel");
   return MIMIC_OK;
 }
 

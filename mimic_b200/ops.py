@@ -231,48 +231,67 @@ def record_gather(src: torch.Tensor, src_row: torch.Tensor, dst: torch.Tensor) -
 class _AlignMSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hp, row_to_compact, row_w, grad_scale, assume_folded, *hs):
-        L = len(hs)
-        h0 = hs[0]
-        D = h0.shape[-1]
-        rows = h0.numel() // D
-        hs = [h if (h.is_contiguous()) else h.contiguous() for h in hs]
-        N = hp.shape[1]
-        dev = h0.device
-        need_grad = any(ctx.needs_input_grad[5:])
-        ptrs = [h.data_ptr() for h in hs]
-        dh = torch.empty((L, rows, D), dtype=h0.dtype, device=dev) if need_grad else None
-        if need_grad:
-            step = rows * D * dh.element_size()
-            ptrs += [dh.data_ptr() + l * step for l in range(L)]
-        ptr_host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
-        ptr_t = torch.empty(len(ptrs), dtype=torch.int64, device=dev)
-        ptr_t.copy_(ptr_host, non_blocking=True)
-        if torch.cuda.is_current_stream_capturing():
-            graph_keepalive.append(ptr_host)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        nbytes = lib.mimic_mse_workspace(L, rows, D)
-        ws = _zero_ws(dev, nbytes, "mse")
-        _ev = timer.start("mse_fwd_bwd")
-        check(lib.mimic_mse_fwd_bwd(ptr_t.data_ptr(), D, _DT[h0.dtype], _ptr(hp), _DT[hp.dtype], _ptr(row_to_compact),
-                                    _ptr(row_w), (ptr_t.data_ptr() + 8 * L) if need_grad else None, float(grad_scale),
-                                    L, rows, N, D, _ptr(loss), _ptr(ws), nbytes, _stream()), "mimic_mse_fwd_bwd")
-        timer.stop(_ev)
-        _count(1)
-        ctx.dh = dh
-        ctx.shapes = [h.shape for h in hs]
-        ctx.grad_scale = grad_scale
-        ctx.assume_folded = assume_folded
-        ctx.keepalive = (ptr_t, ptr_host, hs)
-        return loss[0]
+        return _align_forward(ctx, "mse", hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
 
     @staticmethod
     def backward(ctx, g):
-        dh = ctx.dh
-        if dh is None:
-            return (None,) * (5 + len(ctx.shapes))
-        if not ctx.assume_folded:
-            dh = dh * (g / ctx.grad_scale).to(dh.dtype)
-        return (None, None, None, None, None) + tuple(dh[l].view(s) for l, s in enumerate(ctx.shapes))
+        return _align_backward(ctx, g)
+
+
+class _AlignCos(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hp, row_to_compact, row_w, grad_scale, assume_folded, *hs):
+        return _align_forward(ctx, "cos", hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _align_backward(ctx, g)
+
+
+def _align_forward(ctx, kind, hp, row_to_compact, row_w, grad_scale, assume_folded, *hs):
+    L = len(hs)
+    h0 = hs[0]
+    D = h0.shape[-1]
+    rows = h0.numel() // D
+    hs = [h if (h.is_contiguous()) else h.contiguous() for h in hs]
+    N = hp.shape[1]
+    dev = h0.device
+    need_grad = any(ctx.needs_input_grad[5:])
+    ptrs = [h.data_ptr() for h in hs]
+    dh = torch.empty((L, rows, D), dtype=h0.dtype, device=dev) if need_grad else None
+    if need_grad:
+        step = rows * D * dh.element_size()
+        ptrs += [dh.data_ptr() + l * step for l in range(L)]
+    ptr_host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+    ptr_t = torch.empty(len(ptrs), dtype=torch.int64, device=dev)
+    ptr_t.copy_(ptr_host, non_blocking=True)
+    if torch.cuda.is_current_stream_capturing():
+        graph_keepalive.append(ptr_host)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nbytes = lib.mimic_mse_workspace(L, rows, D)
+    ws = _zero_ws(dev, nbytes, "mse")
+    _ev = timer.start(f"{kind}_fwd_bwd")
+    fn = lib.mimic_mse_fwd_bwd if kind == "mse" else lib.mimic_cos_fwd_bwd
+    check(fn(ptr_t.data_ptr(), D, _DT[h0.dtype], _ptr(hp), _DT[hp.dtype], _ptr(row_to_compact),
+             _ptr(row_w), (ptr_t.data_ptr() + 8 * L) if need_grad else None, float(grad_scale),
+             L, rows, N, D, _ptr(loss), _ptr(ws), nbytes, _stream()), f"mimic_{kind}_fwd_bwd")
+    timer.stop(_ev)
+    _count(1)
+    ctx.dh = dh
+    ctx.shapes = [h.shape for h in hs]
+    ctx.grad_scale = grad_scale
+    ctx.assume_folded = assume_folded
+    ctx.keepalive = (ptr_t, ptr_host, hs)
+    return loss[0]
+
+
+def _align_backward(ctx, g):
+    dh = ctx.dh
+    if dh is None:
+        return (None,) * (5 + len(ctx.shapes))
+    if not ctx.assume_folded:
+        dh = dh * (g / ctx.grad_scale).to(dh.dtype)
+    return (None, None, None, None, None) + tuple(dh[l].view(s) for l, s in enumerate(ctx.shapes))
 
 
 def align_mse(hs: Sequence[torch.Tensor], hp: torch.Tensor, row_to_compact: torch.Tensor, row_w: torch.Tensor,
@@ -282,6 +301,66 @@ def align_mse(hs: Sequence[torch.Tensor], hp: torch.Tensor, row_to_compact: torc
     the upstream gradient of the returned scalar is exactly `grad_scale` (it was folded into dH)."""
     _require_cuda(hp, row_to_compact, row_w, *hs)
     return _AlignMSE.apply(hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
+
+
+def align_cos(hs: Sequence[torch.Tensor], hp: torch.Tensor, row_to_compact: torch.Tensor, row_w: torch.Tensor,
+              grad_scale: float = 1.0, assume_folded: bool = False) -> torch.Tensor:
+    """Layer-wise cosine-similarity loss (Strategy.LAYER_WISE_COS_SIM, src/shift_model.py:152-160): same calling
+    convention as align_mse, with row_w[n] = 1 / (n_samples * L * Nq_sample(n)) (no 1/D)."""
+    _require_cuda(hp, row_to_compact, row_w, *hs)
+    return _AlignCos.apply(hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
+
+
+class _KLLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, y, y_row, grad_scale, assume_folded, inplace):
+        V = z.shape[-1]
+        zz = z.reshape(-1, V)
+        yy = y.reshape(-1, V)
+        if zz.stride(1) != 1:
+            zz = zz.contiguous()
+        if yy.stride(1) != 1:
+            yy = yy.contiguous()
+        R = zz.shape[0]
+        y_row = y_row.reshape(-1).to(torch.int32).contiguous()
+        assert y_row.numel() == R and yy.dtype == zz.dtype
+        dev = zz.device
+        need_grad = ctx.needs_input_grad[0]
+        dz = (zz if inplace else torch.empty_like(zz)) if need_grad else None
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        n_rows = torch.empty(1, dtype=torch.int32, device=dev)
+        nbytes = lib.mimic_ce_workspace(R)
+        ws = _zero_ws(dev, nbytes, "kl")
+        _ev = timer.start("kl_fwd_bwd")
+        check(lib.mimic_kl_fwd_bwd(_ptr(zz), zz.stride(0), _ptr(yy), yy.stride(0), _DT[zz.dtype], _ptr(y_row), _ptr(dz),
+                                   float(grad_scale), R, V, _ptr(loss), _ptr(n_rows), _ptr(ws), nbytes, _stream()),
+              "mimic_kl_fwd_bwd")
+        timer.stop(_ev)
+        _count(1)
+        ctx.dz = dz
+        ctx.shape = z.shape
+        ctx.grad_scale = grad_scale
+        ctx.assume_folded = assume_folded
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.dz
+        if d is None:
+            return (None,) * 6
+        if not ctx.assume_folded:
+            d = d * (g / ctx.grad_scale).to(d.dtype)
+        return d.view(ctx.shape), None, None, None, None, None
+
+
+def kl_loss(shift_logits: torch.Tensor, prefix_logits: torch.Tensor, prefix_row: torch.Tensor, grad_scale: float = 1.0,
+            assume_folded: bool = False, inplace: bool = False) -> torch.Tensor:
+    """KL(softmax(prefix) || softmax(shift)), batchmean over the selected rows (Strategy.LOGITS_KL_DIV,
+    src/shift_model.py:181-191), forward+backward in one launch.  prefix_row[i] = row of prefix_logits.view(-1, V)
+    paired with row i of shift_logits.view(-1, V), or -1 when row i is not selected.  The prefix logits get no gradient
+    (they come from the no-grad context pass)."""
+    _require_cuda(shift_logits, prefix_logits, prefix_row)
+    return _KLLoss.apply(shift_logits, prefix_logits, prefix_row, grad_scale, assume_folded, inplace)
 
 
 class _CELoss(torch.autograd.Function):

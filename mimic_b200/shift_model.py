@@ -58,6 +58,15 @@ def _selected_rows(mask: torch.Tensor, capacity: int):
     return rows, count
 
 
+def _paired_rows(query_mask: torch.Tensor, prefix_mask: torch.Tensor) -> torch.Tensor:
+    """int32 [B*T]: flat row of the context-pass tensor paired with each query row (k-th selected <-> k-th selected,
+    the pairing boolean-mask indexing gives at src/shift_model.py:185-186), -1 on unselected rows.  No host sync."""
+    qf = query_mask.reshape(-1)
+    rows_p, _ = _selected_rows(prefix_mask, qf.numel())
+    rank = (qf.long().cumsum(0) - 1).clamp_min(0)
+    return torch.where(qf, rows_p[rank], torch.full_like(rows_p[rank], -1)).to(torch.int32)
+
+
 class ShiftModel(nn.Module):
     def __init__(self, cfg, shift_encoder, strategy: Strategy, save_checkpoint_when=None) -> None:
         super().__init__()
@@ -138,8 +147,9 @@ class ShiftModel(nn.Module):
         return out
 
     def calculate_layer_wise_loss(self, shift_hidden_states, prefix_hidden_states):   # 145-179
-        if Strategy.LAYER_WISE_MSE not in self.strategy:
-            raise NotImplementedError("only Strategy.LAYER_WISE_MSE is on the CUDA path")
+        cos = Strategy.LAYER_WISE_MSE not in self.strategy     # validate(): exactly one of MSE / COS_SIM (src 147-160)
+        if cos and Strategy.LAYER_WISE_COS_SIM not in self.strategy:
+            raise ValueError("None of layer wise loss strategy is enabled")
         layer_loss = {}
         for (name, shift_list), (_, prefix_list) in zip(shift_hidden_states.items(), prefix_hidden_states.items()):
             per_sample = []
@@ -147,11 +157,18 @@ class ShiftModel(nn.Module):
                 L, n, D = hs.shape
                 hs_c = hs.contiguous()
                 idx = torch.arange(n, dtype=torch.int32, device=hs.device)
-                w = torch.full((n,), 1.0 / (L * n * D), dtype=torch.float32, device=hs.device)
-                per_sample.append(ops.align_mse([hs_c[l] for l in range(L)], hp.contiguous(), idx, w))
+                w = torch.full((n,), 1.0 / (L * n * (1 if cos else D)), dtype=torch.float32, device=hs.device)
+                fn = ops.align_cos if cos else ops.align_mse
+                per_sample.append(fn([hs_c[l] for l in range(L)], hp.contiguous(), idx, w))
             layer_loss[name.replace("hidden_states", self.strategy.layer_wise_strategy())] = \
                 torch.mean(torch.stack(per_sample))
         return layer_loss
+
+    def calculate_logits_kl_loss(self, shift_logits, prefix_logits, query_label_inputs, prefix_label_mask):   # 181-191
+        """F.kl_div(log_softmax(shift_logits[mq]), softmax(prefix_logits[mp]), "batchmean") without the two masked
+        copies: the k-th selected query row is paired with the k-th selected context row inside kernel KL."""
+        return {"logits_kl_loss": ops.kl_loss(shift_logits, prefix_logits,
+                                              _paired_rows(query_label_inputs, prefix_label_mask))}
 
     # ---- the hot path ------------------------------------------------------------------------------
     def forward(self, prefix_texts, query_texts, answers, images):
@@ -187,8 +204,9 @@ class ShiftModel(nn.Module):
         model kwargs containing "input_ids" (attention masks are rebuilt from the pad id like lines
         212/222).  `fold_scale` multiplies every loss gradient (1/accumulate_grad_batches)."""
         enc, tok = self.shift_encoder, self._tok
-        if self.strategy & (Strategy.LOGITS_KL_DIV | Strategy.LAYER_WISE_COS_SIM):
-            raise NotImplementedError("LOGITS_KL_DIV / LAYER_WISE_COS_SIM are not on the CUDA path yet")
+        want_kl = Strategy.LOGITS_KL_DIV in self.strategy
+        cos = Strategy.LAYER_WISE_COS_SIM in self.strategy
+        prefix_logits = prefix_label_mask = None
         loss_dict = {"loss": 0.0}
         hooks = enc.register_record_hooks()
         q_ids = query_inputs["input_ids"]
@@ -214,11 +232,14 @@ class ShiftModel(nn.Module):
                 enc.record_plan = plans
             # step 1: full-context forward, no grad, adapters off (line 225-226); hooks gather H' rows
             enc.key_mask_override = inputs["attention_mask"]
-            if "logits_to_keep" in self._model_forward_params():
+            if not want_kl and "logits_to_keep" in self._model_forward_params():
                 inputs.setdefault("logits_to_keep", 1)      # prefix logits are only read by LOGITS_KL_DIV
             with torch.no_grad(), getattr(self.lmm.model, "disable_adapter", nullcontext)():
-                self.lmm.model(**inputs)
+                out1 = self.lmm.model(**inputs)
             enc.record_plan = None
+            if want_kl:
+                prefix_logits = out1["logits"] if not isinstance(out1, torch.Tensor) else out1
+                prefix_label_mask = self.generate_label_mask(inputs, 2)        # answer + [EOS] rows (line 235)
 
         # step 2: shifted query forward (lines 237-243)
         hooks.update(enc.register_shift_hooks())
@@ -243,19 +264,26 @@ class ShiftModel(nn.Module):
             row_to_compact = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32)
             nq = mq.sum(dim=1).clamp_min(1).float()                               # [B]
             D, L = enc.lmm_hidden_dim, enc.lmm_layers
-            w_row = (1.0 / (B * L * D)) / nq                                      # weight of a row of sample b
+            w_row = (1.0 / (B * L * (1 if cos else D))) / nq                      # weight of a row of sample b
             rows_q, _ = _selected_rows(mq, N_cap)
             row_w = w_row[(rows_q.clamp_min(0) // T).long()]
             aw = float(self.cfg.align_loss_weight)
             layer_loss = {}
             for n in record_names:
                 hs = list(getattr(enc, n))
-                mse = ops.align_mse(hs, self._hp_buffers[n], row_to_compact, row_w,
-                                    grad_scale=aw * fold_scale, assume_folded=True)
-                layer_loss[n.replace("hidden_states", self.strategy.layer_wise_strategy())] = mse
+                align = (ops.align_cos if cos else ops.align_mse)(hs, self._hp_buffers[n], row_to_compact, row_w,
+                                                                  grad_scale=aw * fold_scale, assume_folded=True)
+                layer_loss[n.replace("hidden_states", self.strategy.layer_wise_strategy())] = align
             for k_, v_ in layer_loss.items():
                 loss_dict[k_] = v_.detach()
             loss_dict["loss"] = loss_dict["loss"] + aw * sum(layer_loss.values())
+
+        if want_kl:                                                               # step 4, lines 272-283
+            aw = float(self.cfg.align_loss_weight)
+            kl = ops.kl_loss(logits, prefix_logits, _paired_rows(self.generate_label_mask(query_inputs, 1), prefix_label_mask),
+                             grad_scale=aw * fold_scale, assume_folded=True)
+            loss_dict["logits_kl_loss"] = kl.detach()
+            loss_dict["loss"] = loss_dict["loss"] + aw * kl
 
         self.remove_hooks(hooks)
         return loss_dict

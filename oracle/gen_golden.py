@@ -161,20 +161,32 @@ def gen_loss_pieces():
     hq = model.get_hidden_states(mask_q)
     loss = model.calculate_layer_wise_loss(hq, hp)
     assert list(loss.keys()) == ["ffn_mse_loss"]
-    grads = torch.autograd.grad(loss["ffn_mse_loss"], enc.ffn_hidden_states)
+    grads = torch.autograd.grad(loss["ffn_mse_loss"], enc.ffn_hidden_states, retain_graph=True)
     rec.update(ctx=torch.stack(ctx).numpy(), qry=torch.stack(qry).numpy(), mask_ctx=mask_ctx.numpy(),
                mask_q=mask_q.numpy(), ffn_mse_loss=loss["ffn_mse_loss"].detach().numpy(),
                dqry=torch.stack(grads).numpy(),
                hp0=hp["ffn_hidden_states"][0].numpy(), hp1=hp["ffn_hidden_states"][1].numpy())
     # 3. COS_SIM variant
     model2, _ = make_ref_shift_model(enc, "Strategy.LAYER_WISE_COS_SIM")
-    rec["ffn_cos_sim"] = model2.calculate_layer_wise_loss(hq, hp)["ffn_cos_sim"].detach().numpy()
+    cos = model2.calculate_layer_wise_loss(hq, hp)["ffn_cos_sim"]
+    rec["ffn_cos_sim"] = cos.detach().numpy()
+    rec["dqry_cos"] = torch.stack(torch.autograd.grad(cos, enc.ffn_hidden_states)).numpy()
     # 4. logits KL
     a = torch.randn(7, 50, generator=g)
     b = torch.randn(7, 50, generator=g)
     m = torch.ones(7, dtype=torch.bool)
-    rec.update(kl_a=a.numpy(), kl_b=b.numpy(),
-               kl=model.calculate_logits_kl_loss(a, b, m, m)["logits_kl_loss"].numpy())
+    a.requires_grad_(True)
+    kl = model.calculate_logits_kl_loss(a, b, m, m)["logits_kl_loss"]
+    rec.update(kl_a=a.detach().numpy(), kl_b=b.numpy(), kl=kl.detach().numpy(),
+               dkl_a=torch.autograd.grad(kl, a)[0].numpy())
+    # 4b. ragged selection: 5 of 9 query rows paired with 5 of 11 context rows (boolean-mask order), odd vocabulary
+    a2 = torch.randn(9, 37, generator=g).requires_grad_(True)
+    b2 = torch.randn(11, 37, generator=g)
+    ma = torch.tensor([0, 1, 1, 0, 1, 0, 1, 1, 0], dtype=torch.bool)
+    mb = torch.tensor([1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 1], dtype=torch.bool)
+    kl2 = model.calculate_logits_kl_loss(a2, b2, ma, mb)["logits_kl_loss"]
+    rec.update(kl2_a=a2.detach().numpy(), kl2_b=b2.numpy(), kl2_ma=ma.numpy(), kl2_mb=mb.numpy(), kl2=kl2.detach().numpy(),
+               dkl2_a=torch.autograd.grad(kl2, a2)[0].numpy())
     np.savez_compressed(os.path.join(OUT, "loss_pieces.npz"), **rec)
     print("loss pieces: mse", float(rec["ffn_mse_loss"]), "cos", float(rec["ffn_cos_sim"]), "kl", float(rec["kl"]))
 
@@ -254,7 +266,7 @@ def gen_tiny_step():
     inputs = {"input_ids": full_ids, "attention_mask": full_ids != tok.pad_token_id}
     q_inputs = {"input_ids": qa_ids, "attention_mask": qa_ids != tok.pad_token_id}
     with torch.no_grad():
-        lmm.model(**inputs)
+        prefix_logits = lmm.model(**inputs)["logits"]
     prefix_hs = model.get_hidden_states(model.generate_label_mask(inputs, 1))
     hooks.update(enc.register_shift_hooks())
     logits = lmm.model(**q_inputs)["logits"]
@@ -266,11 +278,22 @@ def gen_tiny_step():
     layer_loss = model.calculate_layer_wise_loss(shift_hs, prefix_hs)
     loss = 0.5 * ce + 1.0 * sum(layer_loss.values())
     params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    # same step under Strategy.LM_LOSS | LAYER_WISE_COS_SIM | LOGITS_KL_DIV (src/shift_model.py:152-160, 181-191, 272-283)
+    model_ck, _ = make_ref_shift_model(enc, "Strategy.LM_LOSS | Strategy.LAYER_WISE_COS_SIM | Strategy.LOGITS_KL_DIV")
+    cos_loss = model_ck.calculate_layer_wise_loss(shift_hs, prefix_hs)
+    kl_loss = model_ck.calculate_logits_kl_loss(logits, prefix_logits, model_ck.generate_label_mask(q_inputs, 1),
+                                                model_ck.generate_label_mask(inputs, 2))
+    loss_ck = 0.5 * ce + 1.0 * sum(cos_loss.values()) + 1.0 * sum(kl_loss.values())
+    grads_ck = torch.autograd.grad(loss_ck, list(params.values()), retain_graph=True)
     grads = torch.autograd.grad(loss, list(params.values()))
-    rec = {"full_ids": full_ids.numpy(), "qa_ids": qa_ids.numpy(), "loss": loss.detach().numpy(),
+    rec = {"cosk.loss": loss_ck.detach().numpy(), "cosk.ffn_cos_sim": cos_loss["ffn_cos_sim"].detach().numpy(),
+           "cosk.logits_kl_loss": kl_loss["logits_kl_loss"].detach().numpy()}
+    for (n, p), gr in zip(params.items(), grads_ck):
+        rec["cosk.grad." + n] = gr.numpy()
+    rec.update({"full_ids": full_ids.numpy(), "qa_ids": qa_ids.numpy(), "loss": loss.detach().numpy(),
            "ce_loss": ce.detach().numpy(), "ffn_mse_loss": layer_loss["ffn_mse_loss"].detach().numpy(),
            "logits_checksum": logits.detach().double().abs().sum().numpy(),
-           "weights_checksum": np.array(sum(float(p.double().abs().sum()) for p in lmm.model.parameters()))}
+           "weights_checksum": np.array(sum(float(p.double().abs().sum()) for p in lmm.model.parameters()))})
     for (n, p), gr in zip(params.items(), grads):
         rec["init." + n] = init[n].numpy()
         rec["grad." + n] = gr.numpy()

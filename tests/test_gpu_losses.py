@@ -95,6 +95,95 @@ def test_align_mse_reference_golden():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(3, 2, 8, 64, (5, 6)), (4, 2, 40, 1024, (33, 17)), (2, 1, 16, 4096, (16,)),
+                                   (2, 1, 6, 8192, (4,))])
+def test_align_cos_matches_oracle(dtype, shape):
+    """Strategy.LAYER_WISE_COS_SIM kernel vs the oracle restatement of src/shift_model.py:152-160."""
+    from mimic_b200 import ops
+    L, B, T, D, counts = shape
+    hs, mask, hp = _mse_case(dtype, L, B, T, D, counts, seed=7)
+    hs32 = [h.float().requires_grad_(True) for h in hs]
+    want = OL.layer_wise_cos_sim(OL.get_hidden_states(hs32, mask),
+                                 [t for t in hp.float().split([int(c) for c in counts], dim=1)])
+    wg = torch.autograd.grad(want, hs32)
+    flat = mask.reshape(-1)
+    rank = flat.long().cumsum(0) - 1
+    r2c = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32).cuda()
+    w_rows = torch.cat([torch.full((c,), 1.0 / (B * L * c)) for c in counts]).cuda()
+    hs_c = [h.cuda().requires_grad_(True) for h in hs]
+    loss = ops.align_cos(hs_c, hp.cuda(), r2c, w_rows)
+    grads = torch.autograd.grad(loss, hs_c)
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b in zip(grads, wg):
+        assert rel(a, b) < tol
+        if not bool(mask.all()):
+            assert float(a[~mask.cuda()].abs().max()) == 0.0
+    with pytest.raises(Exception):                             # one row must fit the CTA's registers
+        big = [torch.zeros(1, 2, 16384, device="cuda")]
+        ops.align_cos(big, torch.zeros(1, 2, 16384, device="cuda"), torch.arange(2, dtype=torch.int32, device="cuda"),
+                      torch.ones(2, device="cuda"))
+
+
+def test_align_cos_and_kl_reference_golden():
+    """The values and gradients the reference itself produced (tests/golden/loss_pieces.npz)."""
+    from mimic_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "loss_pieces.npz"))
+    qry = torch.from_numpy(z["qry"]).cuda()
+    mask_q = torch.from_numpy(z["mask_q"]).bool()
+    hp = torch.cat([torch.from_numpy(z["hp0"]), torch.from_numpy(z["hp1"])], dim=1).cuda()
+    L, B, T, D = qry.shape
+    counts = mask_q.sum(1).tolist()
+    flat = mask_q.reshape(-1)
+    rank = flat.long().cumsum(0) - 1
+    r2c = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32).cuda()
+    w_rows = torch.cat([torch.full((c,), 1.0 / (B * L * c)) for c in counts]).cuda()
+    hs = [qry[l].clone().requires_grad_(True) for l in range(L)]
+    loss = ops.align_cos(hs, hp, r2c, w_rows)
+    assert abs(float(loss) - float(z["ffn_cos_sim"])) < 2e-6
+    assert rel(torch.stack(torch.autograd.grad(loss, hs)), torch.from_numpy(z["dqry_cos"])) < 1e-5
+    # KL, all rows selected
+    a = torch.from_numpy(z["kl_a"]).cuda().requires_grad_(True)
+    rows = torch.arange(a.shape[0], dtype=torch.int32, device="cuda")
+    kl = ops.kl_loss(a, torch.from_numpy(z["kl_b"]).cuda(), rows)
+    assert abs(float(kl) - float(z["kl"])) < 2e-6
+    assert rel(torch.autograd.grad(kl, a)[0], torch.from_numpy(z["dkl_a"])) < 1e-5
+    # KL, ragged pairing built the way ShiftModel does it (no masked copies)
+    from mimic_b200.shift_model import _paired_rows
+    a2 = torch.from_numpy(z["kl2_a"]).cuda().requires_grad_(True)
+    pr = _paired_rows(torch.from_numpy(z["kl2_ma"]).cuda().bool()[None], torch.from_numpy(z["kl2_mb"]).cuda().bool()[None])
+    kl2 = ops.kl_loss(a2, torch.from_numpy(z["kl2_b"]).cuda(), pr)
+    g2, = torch.autograd.grad(kl2, a2)
+    assert abs(float(kl2) - float(z["kl2"])) < 2e-6
+    assert rel(g2, torch.from_numpy(z["dkl2_a"])) < 1e-5
+    assert float(g2[~torch.from_numpy(z["kl2_ma"]).cuda().bool()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (3, 151655), (300, 513)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_kl_matches_oracle(dtype, R, V, inplace):
+    """Strategy.LOGITS_KL_DIV kernel vs F.kl_div (src/shift_model.py:181-191), odd vocabularies, unselected rows."""
+    from mimic_b200 import ops
+    g = torch.Generator().manual_seed(R * 7 + V)
+    zl = (torch.randn(R, V, generator=g) * 3).to(dtype)
+    yl = (torch.randn(R + 5, V, generator=g) * 3).to(dtype)
+    sel = torch.ones(R, dtype=torch.bool)
+    sel[::4] = False
+    y_row = torch.where(sel, torch.randperm(R + 5, generator=g)[:R], torch.full((R,), -1)).to(torch.int32)
+    z32 = zl.float().requires_grad_(True)
+    want = OL.logits_kl(z32[sel], yl.float()[y_row[sel].long()])
+    wg, = torch.autograd.grad(want, z32)
+    zc = zl.cuda().requires_grad_(True)
+    x = zc * 1.0 if inplace else zc
+    loss = ops.kl_loss(x, yl.cuda(), y_row.cuda(), inplace=inplace)
+    got, = torch.autograd.grad(loss, zc)
+    assert abs(float(loss) - float(want)) < 1e-4 * abs(float(want)) + 1e-6
+    assert rel(got, wg) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert float(got[~sel.cuda()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (5, 151655), (300, 513)])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_ce_matches_oracle(dtype, R, V, inplace):

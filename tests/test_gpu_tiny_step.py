@@ -16,6 +16,40 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def _tiny_setup(z, strategy):
+    from oracle.gen_golden import _Tok, tiny_qwen2
+    from mimic_b200 import AttnApproximator, HookedModel, ShiftModel
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = tiny_qwen2()
+    lmm = HookedModel(model.cuda(), "llava-interleave-qwen-7b-hf", processor=types.SimpleNamespace(tokenizer=_Tok()))
+    enc = AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+                           "ShiftStrategy.RECORD_HIDDEN_STATES").cuda()
+    sd = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}
+    enc.load_state_dict(sd, strict=False)
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0,
+                                data=types.SimpleNamespace(num_image_in_query=1))
+    return enc, ShiftModel(cfg, enc, strategy)
+
+
+def test_tiny_step_cos_sim_and_logits_kl_match_reference():
+    """Same step under Strategy.LM_LOSS | LAYER_WISE_COS_SIM | LOGITS_KL_DIV: loss terms and the
+    shift-parameter gradients against what the reference produced (tiny_step.npz, keys cosk.*)."""
+    from mimic_b200 import Strategy
+    z = np.load(os.path.join(GOLDEN, "tiny_step.npz"))
+    enc, sm = _tiny_setup(z, Strategy.LM_LOSS | Strategy.LAYER_WISE_COS_SIM | Strategy.LOGITS_KL_DIV)
+    full_ids, qa_ids = torch.from_numpy(z["full_ids"]).cuda(), torch.from_numpy(z["qa_ids"]).cuda()
+    loss_dict = sm.forward_inputs({"input_ids": full_ids}, {"input_ids": qa_ids})
+    assert set(loss_dict) == {"loss", "ce_loss", "ffn_cos_sim", "logits_kl_loss"}
+    assert abs(float(loss_dict["ffn_cos_sim"]) - float(z["cosk.ffn_cos_sim"])) < 1e-4 * float(z["cosk.ffn_cos_sim"])
+    assert abs(float(loss_dict["logits_kl_loss"]) - float(z["cosk.logits_kl_loss"])) < 1e-3 * float(z["cosk.logits_kl_loss"])
+    assert abs(float(loss_dict["loss"]) - float(z["cosk.loss"])) < 2e-5 * float(z["cosk.loss"])
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    grads = torch.autograd.grad(loss_dict["loss"], list(params.values()))
+    for (n, p), g in zip(params.items(), grads):
+        assert rel(g, z["cosk.grad." + n]) < 5e-4, n
+
+
 def test_tiny_step_matches_reference():
     from oracle.gen_golden import _Tok, tiny_qwen2
     from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy, ops

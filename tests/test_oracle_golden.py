@@ -118,11 +118,20 @@ def test_loss_pieces_match_reference():
     hq = OL.get_hidden_states(qry, g["mask_q"].bool())
     loss = OL.layer_wise_mse(hq, hp)
     assert abs(float(loss.detach()) - float(g["ffn_mse_loss"])) < 1e-6 * abs(float(g["ffn_mse_loss"]))
-    grads = torch.autograd.grad(loss, qry)
+    grads = torch.autograd.grad(loss, qry, retain_graph=True)
     assert rel(torch.stack(grads), g["dqry"]) < 1e-6
-    cos = OL.layer_wise_cos_sim([h.detach() for h in hq], hp)
+    cos = OL.layer_wise_cos_sim(hq, hp)
     assert abs(float(cos) - float(g["ffn_cos_sim"])) < 1e-6
-    assert abs(float(OL.logits_kl(g["kl_a"], g["kl_b"])) - float(g["kl"])) < 1e-6
+    assert rel(torch.stack(torch.autograd.grad(cos, qry)), g["dqry_cos"]) < 1e-6
+    ka = g["kl_a"].clone().requires_grad_(True)
+    kl = OL.logits_kl(ka, g["kl_b"])
+    assert abs(float(kl) - float(g["kl"])) < 1e-6
+    assert rel(torch.autograd.grad(kl, ka)[0], g["dkl_a"]) < 1e-6
+    # ragged pairing: k-th selected query row <-> k-th selected context row (src/shift_model.py:185-186)
+    k2 = g["kl2_a"].clone().requires_grad_(True)
+    kl2 = OL.logits_kl(k2[g["kl2_ma"].bool()], g["kl2_b"][g["kl2_mb"].bool()])
+    assert abs(float(kl2) - float(g["kl2"])) < 1e-6
+    assert rel(torch.autograd.grad(kl2, k2)[0], g["dkl2_a"]) < 1e-6
     # manual formula: mean_i mean_{l,t,d}
     manual = sum(float(((a.detach() - b) ** 2).mean()) for a, b in zip(hq, hp)) / len(hp)
     assert abs(manual - float(g["ffn_mse_loss"])) < 1e-6
