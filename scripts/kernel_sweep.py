@@ -103,6 +103,25 @@ def mse(L, rows, D, dtype=torch.bfloat16):
     return {"L": L, "rows": rows, "D": D, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
 
 
+def cos(L, rows, D, dtype=torch.bfloat16):
+    hs = [torch.randn(rows, D, device=dev).to(dtype).requires_grad_(True) for _ in range(L)]
+    hp = torch.randn(L, rows, D, device=dev).to(dtype)
+    r2c = torch.arange(rows, dtype=torch.int32, device=dev)
+    rw = torch.full((rows,), 1.0 / (L * rows), device=dev)
+    ms = time_kernel(lambda: ops.align_cos(hs, hp, r2c, rw), "cos_fwd_bwd")
+    nbytes = 3 * L * rows * D * hp.element_size()
+    return {"L": L, "rows": rows, "D": D, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+
+
+def kl(R, V):
+    z = (torch.randn(R, V, device=dev) * 2).bfloat16().requires_grad_(True)
+    y = (torch.randn(R, V, device=dev) * 2).bfloat16()
+    rows = torch.arange(R, dtype=torch.int32, device=dev)
+    ms = time_kernel(lambda: ops.kl_loss(z, y, rows), "kl_fwd_bwd")
+    nbytes = 3 * R * V * 2
+    return {"R": R, "V": V, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+
+
 def ce(R, V):
     logits = (torch.randn(R, V, device=dev) * 2).bfloat16().requires_grad_(True)
     labels = torch.randint(0, V, (R,), device=dev)
@@ -128,7 +147,9 @@ if __name__ == "__main__":
         res["mse"] = [mse(32, 256, 4096), mse(32, 4096, 4096)]
         res["ce"] = [ce(256, 32003), ce(1540, 152000)]
         res["gather"] = [gather(6400, 256, 4096), gather(65536, 16384, 4096)]
-        for k in ("mse", "ce", "gather"):
+        res["cos"] = [cos(32, 256, 4096), cos(32, 4096, 4096)]
+        res["kl"] = [kl(256, 32003), kl(1540, 152000)]
+        for k in ("mse", "cos", "ce", "kl", "gather"):
             for r in res[k]:
                 print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in r.items()}, flush=True)
     if which in ("all", "ref"):

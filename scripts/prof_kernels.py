@@ -30,5 +30,17 @@ logits = torch.randn(1540, 152000, device="cuda").bfloat16().requires_grad_(True
 labels = torch.randint(0, 152000, (1540,), device="cuda")
 for _ in range(3):
     ops.ce_loss(logits, labels)
+# Strategy.LAYER_WISE_COS_SIM at the bandwidth shape, Strategy.LOGITS_KL_DIV at the LLaVA logits shape
+hs = [torch.randn(4096, 4096, device="cuda").bfloat16().requires_grad_(True) for _ in range(32)]
+hp = torch.randn(32, 4096, 4096, device="cuda").bfloat16()
+r2c = torch.arange(4096, dtype=torch.int32, device="cuda")
+rw = torch.full((4096,), 1.0 / (32 * 4096), device="cuda")
+for _ in range(3):
+    ops.align_cos(hs, hp, r2c, rw)
+del hs, hp
+prefix = torch.randn(1540, 152000, device="cuda").bfloat16()
+rows = torch.arange(1540, dtype=torch.int32, device="cuda")
+for _ in range(3):
+    ops.kl_loss(logits, prefix, rows)
 torch.cuda.synchronize()
 print("ok")
