@@ -179,6 +179,20 @@ MIMIC_API int mimic_kl_fwd_bwd(const void* z, int64_t z_row_stride, const void* 
                      float* loss, int32_t* n_rows, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Rotary position embedding of q and k in ONE launch: the RoPE step of the replaced attention forwards
+ * (src/shift_encoder.py:307-312, 417-422, 495-501; HF apply_rotary_pos_emb: x*cos + rotate_half(x)*sin).
+ *   q [B,T,H,d], k [B,T,Hkv,d] read through element strides (*_sb batch, *_st token, *_sh head; head_dim stride 1):
+ *   the q/k projection outputs are consumed where they lie.  cos, sin [B,T,d] (c_sb, c_st; c_sb = 0 broadcasts).
+ *   q_out [B,T,H,d], k_out [B,T,Hkv,d] contiguous (may alias the inputs when those are contiguous).
+ *   inverse != 0 applies the transpose (the backward: d/dx of the rotation).   d % 16 == 0.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_rope_qk(const void* q, int64_t q_sb, int64_t q_st, int64_t q_sh,
+                  const void* k, int64_t k_sb, int64_t k_st, int64_t k_sh,
+                  const void* cos, const void* sin, int64_t c_sb, int64_t c_st,
+                  void* q_out, void* k_out, int32_t dtype,
+                  int32_t B, int32_t T, int32_t H, int32_t Hkv, int32_t d, int32_t inverse, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * On-device optimizer step for the flat fp32 shift-parameter buffer: global-norm clip
  * (train.yaml grad_clip_val) + AdamW with per-element weight decay (the reference's two groups,
  * src/shift_model.py:306-372: names containing "bias" get 0).  Replaces DeepSpeedCPUAdam's host

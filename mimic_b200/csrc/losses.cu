@@ -732,6 +732,55 @@ __global__ void __launch_bounds__(512) kl_fwd_bwd_kernel(const T* __restrict__ z
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rotary embedding of q and k in one pass (the RoPE step of the replaced attention forwards,
+// src/shift_encoder.py:307-312, 417-422, 495-501: q*cos + rotate_half(q)*sin done by ~10 elementwise launches in
+// the HF code).  Reads q [B,T,H,d] and k [B,T,Hkv,d] through their strides (the projection outputs, in place of any
+// .contiguous()), writes contiguous outputs:  y_lo = x_lo c_lo - x_hi s_lo,  y_hi = x_hi c_hi + x_lo s_hi.
+// inverse = the transpose (backward):        dx_lo = g_lo c_lo + g_hi s_hi,  dx_hi = g_hi c_hi - g_lo s_lo.
+// Algorithmic bytes: 2 * (H + Hkv) * d * sizeof(T) per token (+ cos/sin once per token, L1-resident across heads).
+template <typename T>
+__global__ void __launch_bounds__(256) rope_qk_kernel(const T* __restrict__ q, int64_t q_sb, int64_t q_st, int64_t q_sh,
+                                                      const T* __restrict__ k, int64_t k_sb, int64_t k_st, int64_t k_sh,
+                                                      const T* __restrict__ cosp, const T* __restrict__ sinp, int64_t c_sb,
+                                                      int64_t c_st, T* __restrict__ q_out, T* __restrict__ k_out, int B, int Tn,
+                                                      int H, int Hkv, int d, int inverse) {
+  const int half = d / 2, cpr = half / 8;              // 8-element chunks per half row
+  const int items = (H + Hkv) * cpr;
+  const int64_t tokens = (int64_t)B * Tn;
+  for (int64_t tok = blockIdx.x; tok < tokens; tok += gridDim.x) {
+    const int b = (int)(tok / Tn), t = (int)(tok % Tn);
+    const T* cr = cosp + b * c_sb + t * c_st;
+    const T* sr = sinp + b * c_sb + t * c_st;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int head = it / cpr, c = it - head * cpr;
+      const bool is_q = head < H;
+      const int hh = is_q ? head : head - H;
+      const T* src = is_q ? q + b * q_sb + t * q_st + hh * q_sh : k + b * k_sb + t * k_st + hh * k_sh;
+      T* dst = is_q ? q_out + (tok * H + hh) * d : k_out + (tok * Hkv + hh) * d;
+      float lo[8], hi[8], cl[8], ch[8], sl[8], sh[8], ol[8], oh[8];
+      load8(src + 8 * c, lo);
+      load8(src + half + 8 * c, hi);
+      load8(cr + 8 * c, cl);
+      load8(cr + half + 8 * c, ch);
+      load8(sr + 8 * c, sl);
+      load8(sr + half + 8 * c, sh);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (inverse) {
+          ol[e] = fmaf(lo[e], cl[e], hi[e] * sh[e]);
+          oh[e] = fmaf(hi[e], ch[e], -lo[e] * sl[e]);
+        } else {
+          ol[e] = fmaf(lo[e], cl[e], -hi[e] * sl[e]);
+          oh[e] = fmaf(hi[e], ch[e], lo[e] * sh[e]);
+        }
+      }
+      Chunk<T>::store(dst + 8 * c, ol);
+      Chunk<T>::store(dst + half + 8 * c, oh);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // clip + AdamW on the flat fp32 parameter buffer
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ grad, int64_t n, float grad_mul, float* __restrict__ sumsq) {
   __shared__ float red[32];
@@ -924,6 +973,35 @@ extern "C" int mimic_kl_fwd_bwd(const void* z, int64_t z_row_stride, const void*
     return MIMIC_ERR_UNSUPPORTED;
   }
   MIMIC_LAUNCH_OK("kl_fwd_bwd_kernel");
+  return MIMIC_OK;
+}
+
+extern "C" int mimic_rope_qk(const void* q, int64_t q_sb, int64_t q_st, int64_t q_sh, const void* k, int64_t k_sb, int64_t k_st,
+                             int64_t k_sh, const void* cosp, const void* sinp, int64_t c_sb, int64_t c_st, void* q_out,
+                             void* k_out, int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t Hkv, int32_t d,
+                             int32_t inverse, void* stream) {
+  MIMIC_CHECK_ARG(q && k && cosp && sinp && q_out && k_out, "NULL argument");
+  MIMIC_CHECK_ARG(B > 0 && T > 0 && H > 0 && Hkv > 0 && d > 0 && d % 16 == 0, "bad shape (head_dim must be a multiple of 16)");
+  const int64_t al = dtype == MIMIC_BF16 ? 8 : 4;      // 16-byte rows
+  MIMIC_CHECK_ARG(q_sb % al == 0 && q_st % al == 0 && q_sh % al == 0 && k_sb % al == 0 && k_st % al == 0 && k_sh % al == 0 &&
+                      c_sb % al == 0 && c_st % al == 0,
+                  "strides must keep rows 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t tokens = (int64_t)B * T;
+  const int grid = (int)(tokens < (int64_t)num_sms() * 8 ? tokens : (int64_t)num_sms() * 8);
+  if (dtype == MIMIC_BF16)
+    rope_qk_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, q_sb, q_st, q_sh, (const __nv_bfloat16*)k, k_sb,
+                                                        k_st, k_sh, (const __nv_bfloat16*)cosp, (const __nv_bfloat16*)sinp, c_sb,
+                                                        c_st, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_out, B, T, H, Hkv, d, inverse);
+  else if (dtype == MIMIC_F32)
+    rope_qk_kernel<float><<<grid, 256, 0, st>>>((const float*)q, q_sb, q_st, q_sh, (const float*)k, k_sb, k_st, k_sh,
+                                                (const float*)cosp, (const float*)sinp, c_sb, c_st, (float*)q_out, (float*)k_out,
+                                                B, T, H, Hkv, d, inverse);
+  else {
+    set_error("rope: unsupported dtype %d", dtype);
+    return MIMIC_ERR_UNSUPPORTED;
+  }
+  MIMIC_LAUNCH_OK("rope_qk_kernel");
   return MIMIC_OK;
 }
 

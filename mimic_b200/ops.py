@@ -212,6 +212,53 @@ def shifted_attention(q, k, v, shift=None, w=None, bias=None, key_mask=None, *, 
 
 
 # ------------------------------------------------------------------------------------------------
+def _rope_launch(q, k, cos, sin, inverse: bool):
+    """q [B,T,H,d], k [B,T,Hkv,d] (any strides with unit head-dim stride) -> contiguous rotated copies."""
+    B, T, H, d = q.shape
+    Hkv = k.shape[2]
+    if q.stride(3) != 1:
+        q = q.contiguous()
+    if k.stride(3) != 1:
+        k = k.contiguous()
+    cos = cos.to(q.dtype)
+    sin = sin.to(q.dtype)
+    if cos.dim() == 2:
+        cos, sin = cos[None], sin[None]
+    if cos.stride(-1) != 1 or sin.stride() != cos.stride():
+        cos, sin = cos.contiguous(), sin.contiguous()
+    c_sb = 0 if cos.shape[0] == 1 else cos.stride(0)
+    q_out = torch.empty((B, T, H, d), dtype=q.dtype, device=q.device)
+    k_out = torch.empty((B, T, Hkv, d), dtype=k.dtype, device=k.device)
+    _ev = timer.start("rope_qk")
+    check(lib.mimic_rope_qk(_ptr(q), q.stride(0), q.stride(1), q.stride(2), _ptr(k), k.stride(0), k.stride(1), k.stride(2),
+                            _ptr(cos), _ptr(sin), c_sb, cos.stride(1), _ptr(q_out), _ptr(k_out), _DT[q.dtype],
+                            B, T, H, Hkv, d, int(inverse), _stream()), "mimic_rope_qk")
+    timer.stop(_ev)
+    _count(1)
+    return q_out, k_out
+
+
+class _RopeQK(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        return _rope_launch(q, k, cos, sin, False)
+
+    @staticmethod
+    def backward(ctx, gq, gk):
+        cos, sin = ctx.saved_tensors
+        dq, dk = _rope_launch(gq, gk, cos, sin, True)
+        return dq, dk, None, None
+
+
+def rope_qk(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor):
+    """HF apply_rotary_pos_emb on q [B,T,H,d] and k [B,T,Hkv,d] (token-major views of the projection outputs) with
+    cos/sin [B,T,d] (or [T,d]): ONE launch instead of ~10 elementwise ones; returns contiguous [B,T,H,d], [B,T,Hkv,d].
+    Differentiable w.r.t. q and k (the backward is the transposed rotation, same kernel)."""
+    _require_cuda(q, k, cos, sin)
+    return _RopeQK.apply(q, k, cos, sin)
+
+
 def record_gather(src: torch.Tensor, src_row: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[n,:] = src.view(-1,D)[src_row[n],:]   (kernel R; src_row int32 on device)."""
     _require_cuda(src, src_row, dst)

@@ -210,18 +210,26 @@ def _fused_attn_forward(self, hidden_states, position_embeddings=None, attention
         raise NotImplementedError("sliding-window attention is not supported by the fused shifted attention")
     B, T, _ = hidden_states.shape
     d = self.head_dim
-    q = self.q_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
-    k = self.k_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+    q = self.q_proj(hidden_states).view(B, T, -1, d)   # token-major [B,T,H,d]: RoPE kernel and attention read it in place
+    k = self.k_proj(hidden_states).view(B, T, -1, d)
     v = self.v_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
     cache = past_key_values if past_key_values is not None else past_key_value
+    cos = sin = None
     if position_embeddings is not None:
         cos, sin = position_embeddings
-        q, k = _apply_rope(q, k, cos, sin)
     elif hasattr(self, "rotary_emb"):                  # pre-4.48 module layout (Idefics v1)
         kv_len = T + (cache.get_seq_length(self.layer_idx) if cache is not None else 0)
         cos, sin = self.rotary_emb(v, seq_len=max(kv_len, T))
         pos = position_ids if position_ids is not None else torch.arange(kv_len - T, kv_len, device=q.device)[None]
-        q, k = _apply_rope(q, k, cos[pos], sin[pos])
+        cos, sin = cos[pos], sin[pos]
+    if cos is not None:
+        if cos.shape[-1] == d:
+            q, k = ops.rope_qk(q, k, cos, sin)         # one launch for q and k (HF: ~10 elementwise kernels)
+            q, k = q.transpose(1, 2), k.transpose(1, 2)
+        else:                                          # partial rotary factor: not a shape of the three target backbones
+            q, k = _apply_rope(q.transpose(1, 2), k.transpose(1, 2), cos, sin)
+    else:
+        q, k = q.transpose(1, 2), k.transpose(1, 2)
     if cache is not None:
         k, v = cache.update(k, v, self.layer_idx)
     if getattr(self, "qk_layer_norms", False):         # Idefics v1 option (src/shift_encoder.py:328-330)

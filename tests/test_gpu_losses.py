@@ -224,6 +224,39 @@ def test_ce_all_ignored_and_lm_rule():
     assert abs(float(got) - float(want)) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,H,Hkv,d,bcast", [(2, 9, 8, 2, 128, False), (1, 33, 4, 4, 64, True), (3, 5, 32, 8, 128, False)])
+def test_rope_qk_matches_hf_formula(dtype, B, T, H, Hkv, d, bcast):
+    """One-launch RoPE vs HF apply_rotary_pos_emb (x*cos + rotate_half(x)*sin), strided projection-output views,
+    forward and backward (the transposed rotation)."""
+    from mimic_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + T)
+    qkv = torch.randn(B, T, (H + 2 * Hkv) * d, generator=g).to(dtype)      # a fused projection: q and k are strided views
+    q = qkv[..., : H * d].view(B, T, H, d)
+    k = qkv[..., H * d: (H + Hkv) * d].view(B, T, Hkv, d)
+    pos = torch.arange(T)[None].expand(1 if bcast else B, T) + (0 if bcast else torch.arange(B)[:, None] * 3)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, d, 2).float() / d))
+    ang = pos[..., None].float() * inv
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().to(dtype), emb.sin().to(dtype)
+
+    def rot(x):
+        return torch.cat((-x[..., d // 2:], x[..., : d // 2]), -1)
+
+    q32, k32 = q.float().requires_grad_(True), k.float().requires_grad_(True)
+    c32, s32 = cos.float()[:, :, None], sin.float()[:, :, None]
+    wq, wk = q32 * c32 + rot(q32) * s32, k32 * c32 + rot(k32) * s32
+    gq, gk = torch.randn(B, T, H, d, generator=g), torch.randn(B, T, Hkv, d, generator=g)
+    wdq, wdk = torch.autograd.grad([wq, wk], [q32, k32], [gq, gk])
+    qc, kc = q.cuda().requires_grad_(True), k.cuda().requires_grad_(True)
+    oq, ok = ops.rope_qk(qc, kc, cos.cuda(), sin.cuda())
+    assert oq.shape == (B, T, H, d) and ok.shape == (B, T, Hkv, d) and oq.is_contiguous()
+    tol = 1e-6 if dtype == torch.float32 else 6e-3
+    assert rel(oq, wq) < tol and rel(ok, wk) < tol
+    dq, dk = torch.autograd.grad([oq, ok], [qc, kc], [gq.cuda().to(dtype), gk.cuda().to(dtype)])
+    assert rel(dq, wdq) < tol and rel(dk, wdk) < tol
+
+
 def test_adamw_step_matches_torch():
     from mimic_b200 import ops
     torch.manual_seed(0)
