@@ -21,7 +21,10 @@ COLS = [("gpu__time_duration.sum", "duration"),
 
 
 def main(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):                        # already exported on the GPU box (ncu -i rep --page raw --csv)
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {n: i for i, n in enumerate(hdr)}

@@ -42,5 +42,11 @@ prefix = torch.randn(1540, 152000, device="cuda").bfloat16()
 rows = torch.arange(1540, dtype=torch.int32, device="cuda")
 for _ in range(3):
     ops.kl_loss(logits, prefix, rows)
+# RoPE of q and k at the context-pass shape (B=2, T=3200, H=32, Hkv=8, d=128), strided projection-output views
+qkv = torch.randn(2, 3200, (32 + 16) * 128, device="cuda").bfloat16()
+qv, kv_ = qkv[..., : 32 * 128].view(2, 3200, 32, 128), qkv[..., 32 * 128: 40 * 128].view(2, 3200, 8, 128)
+cs = torch.randn(2, 3200, 128, device="cuda").bfloat16()
+for _ in range(3):
+    ops.rope_qk(qv, kv_, cs, cs)
 torch.cuda.synchronize()
 print("ok")
