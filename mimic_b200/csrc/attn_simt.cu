@@ -238,37 +238,50 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
   const E* qb = reinterpret_cast<const E*>(p.q) + b * p.q_sb + h * p.q_sh;
   const int64_t row0 = ((int64_t)b * p.H + h) * T;
 
-  for (int r = warp; r < 64; r += 4) {
-    const int t = t0 + r;
-    float dmu = 0.f, gout = 0.f;
-    if (t < T) {
+  // rows r = warp + 4 i: four rows per batch, all their loads issued before the first reduction (a launch at T = 128 is
+  // pure latency: 16 serial row trips per warp cost more than the tensor-core kernel that follows)
+  for (int r4 = 0; r4 < 16; r4 += 4) {
+    float gv[4][EPL], ov[4][EPL];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + warp + 4 * (r4 + i);
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         const int c = lane * EPL + e;
-        const float g = to_f32(gb[(int64_t)t * p.go_st + c]);
-        gout += g * to_f32(ob[(int64_t)t * p.o_st + c]);
-        if (p.active) dmu += g * p.shift[h * D + c];
+        gv[i][e] = t < T ? to_f32(gb[(int64_t)t * p.go_st + c]) : 0.f;
+        ov[i][e] = t < T ? to_f32(ob[(int64_t)t * p.o_st + c]) : 0.f;
       }
     }
-    dmu = warp_sum(dmu);
-    gout = warp_sum(gout);
-    if (lane == 0) {
-      float mu = 0.f, dz = 0.f, dl = 0.f;
-      if (t < T) {
-        if (p.active) {
-          mu = p.mu[row0 + t];
-          dz = mu * (1.f - mu) * dmu;
-          const float lc = p.lse_c[row0 + t];
-          const float rho = (lc == -INFINITY) ? 0.f : expf(lc - p.lse_full[row0 + t]);
-          dl = gout - mu * dmu + dz * rho;
-        } else {
-          dl = gout;
-        }
-        p.delta_ws[row0 + t] = dl;
-        p.dz_ws[row0 + t] = dz;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 4 * (r4 + i);
+      const int t = t0 + r;
+      float dmu = 0.f, gout = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        gout += gv[i][e] * ov[i][e];
+        if (p.active) dmu += gv[i][e] * p.shift[h * D + lane * EPL + e];
       }
-      mu_s[r] = mu;
-      dz_s[r] = dz;
+      dmu = warp_sum(dmu);
+      gout = warp_sum(gout);
+      if (lane == 0) {
+        float mu = 0.f, dz = 0.f, dl = 0.f;
+        if (t < T) {
+          if (p.active) {
+            mu = p.mu[row0 + t];
+            dz = mu * (1.f - mu) * dmu;
+            const float lc = p.lse_c[row0 + t];
+            const float rho = (lc == -INFINITY) ? 0.f : expf(lc - p.lse_full[row0 + t]);
+            dl = gout - mu * dmu + dz * rho;
+          } else {
+            dl = gout;
+          }
+          p.delta_ws[row0 + t] = dl;
+          p.dz_ws[row0 + t] = dz;
+        }
+        mu_s[r] = mu;
+        dz_s[r] = dz;
+      }
     }
   }
   __syncthreads();
@@ -276,13 +289,21 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
     const int c = tid;
     float acc_s = 0.f, acc_w = 0.f;
     const float wv = p.active ? p.w[h * D + c] : 0.f;
-    for (int r = 0; r < 64; ++r) {
-      const int t = t0 + r;
-      if (t >= T) break;
-      p.dq_acc[(row0 + t) * D + c] = dz_s[r] * wv * p.dq_seed_mul;
-      if (p.active) {
-        acc_s += mu_s[r] * to_f32(gb[(int64_t)t * p.go_st + c]);
-        acc_w += dz_s[r] * to_f32(qb[(int64_t)t * p.q_st + c]);
+    for (int r0 = 0; r0 < 64; r0 += 8) {                 // eight rows of g and q in flight per thread
+      float g8[8], q8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = t0 + r0 + i;
+        const bool in = p.active && t < T;
+        g8[i] = in ? to_f32(gb[(int64_t)t * p.go_st + c]) : 0.f;
+        q8[i] = in ? to_f32(qb[(int64_t)t * p.q_st + c]) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i, t = t0 + r;
+        if (t < T) p.dq_acc[(row0 + t) * D + c] = dz_s[r] * wv * p.dq_seed_mul;
+        acc_s += mu_s[r] * g8[i];
+        acc_w += dz_s[r] * q8[i];
       }
     }
     if (p.active) {

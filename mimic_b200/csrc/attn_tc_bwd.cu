@@ -41,14 +41,14 @@ constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
 constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
 constexpr int STAGE_BYTES = 32 * HD * 4;   // fp32 dQ staging for 32 query rows, 16 KB (two bulk reduces per tile)
 constexpr int NQS = 3;                     // Q / dO TMA stages
-constexpr int THREADS = 704;                // warp 0 TMA, warp 1 MMA, warps 2-9 / 10-17 softmax groups 0 / 1, warps 18-21 drain
+constexpr int THREADS = 736;                // warp 0 TMA, warps 1 / 22 MMA issuers A / B, warps 2-9 / 10-17 softmax groups 0 / 1, warps 18-21 drain
 constexpr float LOG2E = 1.4426950408889634f;
 
 constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + NQS * Q_TILE, OFF_DS = OFF_DO + NQS * Q_TILE,
               OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 4 * BQ * 16,
               OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16;
 
-enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, N_BARS = 16 };
+enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, DK_DONE = 16, N_BARS = 18 };
 
 constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_SDQ = 256, TM_DP = 384;
 constexpr uint32_t IDESC_ST = idesc_bf16(128, BQ, 0, 0);     // S^T, dP^T : A, B K-major
@@ -116,6 +116,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_init(&bars[SOFT_DONE + i], 256);
         mbar_init(&bars[DQ_FULL + i], 1);
         mbar_init(&bars[DRAIN_DONE + i], 128);
+        mbar_init(&bars[DK_DONE + i], 1);
       }
       mbar_init(&bars[DKV_FULL], 1);
       fence_barrier_init();
@@ -167,8 +168,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 22) {
+    // ===================== two MMA issuers =====================
+    // The single issuing warp was the bottleneck (instruction latency of one warp: ~8.7 cycles per instruction, ~350
+    // instructions per iteration).  The stream is split by operand, not by iteration, so each accumulator keeps ONE issuer:
+    //   warp 1  (A):  dV(i)  dQ^T(i) | commit DQ_FULL   dK(i) | commit DK_DONE[st], QDO_EMPTY        after SOFT_DONE(i)
+    //   warp 22 (B):  dP^T(i+2)  after DK_DONE(i)   (dK(i) has read dS^T(i) out of dP[st])
+    //                 S^T(i+2)   after DRAIN_DONE(i) (the drain warps emptied dQ^T(i) out of SdQ[st]) | commit S_FULL
+    // Every cross-issuer hazard is an explicit mbarrier; inside one issuer the tensor pipe runs in issue order.
     // All 32 lanes run the control flow (waits, address arithmetic stay warp-uniform); one elected lane issues.
     if (n > 0) {
       constexpr uint32_t HI = desc_hi_sw128(1024);
@@ -177,116 +184,97 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t q_km0 = desc_lo(smem_u32(sQ), 16), do_km0 = desc_lo(smem_u32(sDO), 16);
       const uint32_t q_mn0 = desc_lo(smem_u32(sQ), Q_HALF), do_mn0 = desc_lo(smem_u32(sDO), Q_HALF);
       const uint32_t ds_mn0 = desc_lo(smem_u32(sDS), 16);
-      mbar_wait(&bars[KV_FULL], 0, 200);
-      // Tensor-pipe order per iteration i (st = i & 1):
-      //   dV(i)  dQ^T(i) | commit DQ_FULL  dK(i) | commit QDO_EMPTY  dP^T(i+2)  [DRAIN_DONE(i)]  S^T(i+2) | commit S_FULL
-      // dQ^T(i) lands in SdQ[st] over P^T(i) (dV(i) has read it: the pipe runs in issue order); the drain warps empty it
-      // while dK(i) and dP^T(i+2) run, so S^T(i+2) can be issued into the same columns without draining the pipe.
-      // All loop bookkeeping is incremental (no div/mod on the issue path).
-      auto issue_dp = [&](int st2, int qs2) {            // dP^T = V dO^T -> dP[st2]   (elected lane)
-        const uint32_t do_km = do_km0 + qs2 * (Q_TILE >> 4), d_p = tmem_base + TM_DP + st2 * BQ;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
-          if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-          else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-        }
-      };
-      auto issue_s = [&](int st2, int qs2) {             // S^T = K Q^T -> SdQ[st2], then S_FULL   (elected lane)
-        const uint32_t q_km = q_km0 + qs2 * (Q_TILE >> 4), d_s = tmem_base + TM_SDQ + st2 * BQ;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
-          if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
-          else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
-        }
-        tc_commit(&bars[S_FULL + st2]);
-      };
       auto next_qt = [&](int qt) { return qt + 1 == n_qt ? qt_first : qt + 1; };
-      int qt_i = qt_first;                       // query tile of iteration i
-      int qt_2 = qt_first;                       // query tile of iteration i + 2
-      int qs = 0, qs2 = 0, qph2 = 0;             // Q/dO ring stage of iteration i; stage and phase of iteration i + 2
-      auto advance2 = [&]() {
-        qt_2 = next_qt(qt_2);
-        if (++qs2 == NQS) {
-          qs2 = 0;
-          qph2 ^= 1;
+      mbar_wait(&bars[KV_FULL], 0, 200);
+      if (warp == 22) {
+        // ---------------- issuer B: S^T / dP^T of iteration i2 = 0 .. n-1 ----------------
+        int qt2 = qt_first, qs2 = 0, qph2 = 0;
+        for (int i2 = 0; i2 < n; ++i2) {
+          const int st2 = i2 & 1;
+          const bool nc2 = need_c(qt2);
+          const uint32_t prev_par = ((i2 >> 1) & 1) ^ 1;       // parity of the phase completed by iteration i2 - 2 (passes for i2 < 2)
+          mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
+          if (lane == 0) stamp(5, i2, 0);
+          if (nc2) {
+            mbar_wait(&bars[DK_DONE + st2], prev_par, 212 + st2);
+            if (lane == 0) stamp(5, i2, 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t do_km = do_km0 + qs2 * (Q_TILE >> 4), d_p = tmem_base + TM_DP + st2 * BQ;
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+                if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+                else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+              }
+            }
+            __syncwarp();
+          }
+          if (!dbg(2)) mbar_wait(&bars[DRAIN_DONE + st2], prev_par, 215 + st2);
+          if (!nc2) mbar_wait(&bars[DK_DONE + st2], prev_par, 213 + st2);   // S_FULL below also frees dP[st2] for the softmax group
+          if (lane == 0) stamp(5, i2, 2);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t q_km = q_km0 + qs2 * (Q_TILE >> 4), d_s = tmem_base + TM_SDQ + st2 * BQ;
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+              if (k == 0) mma_ss_c<false>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
+              else mma_ss_c<true>(d_s, desc64(HI, k_km + ko_kv), desc64(HI, q_km + ko_q), IDESC_ST);
+            }
+            tc_commit(&bars[S_FULL + st2]);
+          }
+          __syncwarp();
+          if (lane == 0) stamp(5, i2, 3);
+          qt2 = next_qt(qt2);
+          if (++qs2 == NQS) {
+            qs2 = 0;
+            qph2 ^= 1;
+          }
         }
-      };
-      // prologue: S^T / dP^T of iterations 0 and 1 (their TMEM buffers are fresh)
-      for (int i2 = 0; i2 < 2 && i2 < n; ++i2) {
-        mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
-        if (lane == 0) stamp(1, i2, 0);
-        tc_fence_after();
-        if (elect_one()) {
-          if (need_c(qt_2)) issue_dp(i2, qs2);
-          issue_s(i2, qs2);
-        }
-        __syncwarp();
-        if (lane == 0) stamp(1, i2, 2);
-        advance2();
-      }
-      bool dv_started = false;
-      for (int i = 0; i < n; ++i) {
-        const int st = i & 1;
-        const bool nc = need_c(qt_i);
-        const bool has2 = i + 2 < n;
-        const bool nc2 = has2 && need_c(qt_2);
-        if (lane == 0) stamp(5, i, 0);
-        // Q/dO of iteration i+2 landed a full iteration ago in steady state: taking this wait here keeps it off the
-        // stretch between the last dK MMA and the first dP^T MMA
-        if (has2) mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
-        if (lane == 0) stamp(1, i + 2, 0);
-        mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
-        if (lane == 0) stamp(1, i, 3);
-        tc_fence_after();
-        if (lane == 0) stamp(5, i, 1);
-        if (elect_one()) {
-          stamp(5, i, 2);
-          const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
-          const uint32_t ds_mn = ds_mn0 + st * (DS_TILE >> 4);
-          const uint32_t a_p = tmem_base + TM_SDQ + st * BQ, a_ds = tmem_base + TM_DP + st * BQ;
-          if (nc) {
-            // dV += P^T dO_i : K = 16 queries per step; step k's 8 packed TMEM cols sit at [16k, 16k+8) of the buffer
+      } else {
+        // ---------------- issuer A: dV / dQ^T / dK of iteration i ----------------
+        int qt_i = qt_first, qs = 0;
+        bool dv_started = false;
+        for (int i = 0; i < n; ++i) {
+          const int st = i & 1;
+          const bool nc = need_c(qt_i);
+          mbar_wait(&bars[SOFT_DONE + st], (i >> 1) & 1, 220 + st);
+          if (lane == 0) stamp(1, i, 3);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t q_mn = q_mn0 + qs * (Q_TILE >> 4), do_mn = do_mn0 + qs * (Q_TILE >> 4);
+            const uint32_t ds_mn = ds_mn0 + st * (DS_TILE >> 4);
+            const uint32_t a_p = tmem_base + TM_SDQ + st * BQ, a_ds = tmem_base + TM_DP + st * BQ;
+            if (nc) {
+              // dV += P^T dO_i : K = 16 queries per step; step k's 8 packed TMEM cols sit at [16k, 16k+8) of the buffer
+#pragma unroll
+              for (int k = 0; k < BQ / 16; ++k)
+                mma_ts(tmem_base + TM_DV, a_p + 16 * k, desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || dv_started) ? 1u : 0u);
+            }
+            // dQ^T = K^T dS^T : K = 16 keys per step; overwrites P^T(i) in SdQ[st] (dV(i) has read it: pipe order)
+#pragma unroll
+            for (int k = 0; k < BN / 16; ++k) {
+              if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
+              else mma_ss_c<true>(a_p, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
+            }
+            tc_commit(&bars[DQ_FULL + st]);
+            // dK += dS^T Q_i
 #pragma unroll
             for (int k = 0; k < BQ / 16; ++k)
-              mma_ts(tmem_base + TM_DV, a_p + 16 * k, desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || dv_started) ? 1u : 0u);
+              mma_ts(tmem_base + TM_DK, a_ds + 16 * k, desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || i > 0) ? 1u : 0u);
+            tc_commit(&bars[DK_DONE + st]);
+            tc_commit(&bars[QDO_EMPTY + qs]);
           }
-          // dQ^T = K^T dS^T : K = 16 keys per step; overwrites P^T(i) in SdQ[st]
-#pragma unroll
-          for (int k = 0; k < BN / 16; ++k) {
-            if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
-            else mma_ss_c<true>(a_p, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
-          }
-          tc_commit(&bars[DQ_FULL + st]);
-          stamp(5, i, 3);
-          // dK += dS^T Q_i
-#pragma unroll
-          for (int k = 0; k < BQ / 16; ++k)
-            mma_ts(tmem_base + TM_DK, a_ds + 16 * k, desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || i > 0) ? 1u : 0u);
-          tc_commit(&bars[QDO_EMPTY + qs]);
-          stamp(5, i, 4);
-          if (nc2) issue_dp(st, qs2);                      // dP^T(i+2) over dS^T(i): dK(i) has read it (pipe order)
-          stamp(5, i, 5);
-        }
-        __syncwarp();
-        if (lane == 0) stamp(1, i, 4);
-        if (nc) dv_started = true;
-        if (has2) {
-          if (!dbg(2)) mbar_wait(&bars[DRAIN_DONE + st], (i >> 1) & 1, 215 + st);   // dQ^T(i) left SdQ[st]
-          if (lane == 0) stamp(1, i + 2, 1);
-          tc_fence_after();
-          if (lane == 0) stamp(5, i, 6);
-          if (elect_one()) issue_s(st, qs2);
           __syncwarp();
-          if (lane == 0) stamp(1, i + 2, 2);
-          advance2();
+          if (lane == 0) stamp(1, i, 4);
+          if (nc) dv_started = true;
+          qt_i = next_qt(qt_i);
+          if (++qs == NQS) qs = 0;
         }
-        qt_i = next_qt(qt_i);
-        if (++qs == NQS) qs = 0;
+        if (elect_one()) tc_commit(&bars[DKV_FULL]);
+        __syncwarp();
       }
-      if (elect_one()) tc_commit(&bars[DKV_FULL]);
-      __syncwarp();
     }
   } else if (warp < 18) {
     // ===================== softmax warps: two ping-pong groups of 8 warps =====================

@@ -20,10 +20,10 @@ torch.cuda.synchronize()
 _lib.lib.mimic_debug_set_trace(None, 0)
 t = buf.cpu().view(24, 8, 8)
 t0 = int(t[t > 0].min())
-roles = {0: ("producer", ["empty", "issued", "landed"]), 1: ("mma", ["sdp:wait_qdo", "sdp:wait_drain", "sdp:issued", "soft_done", "dvdkdq:issued"]),
+roles = {0: ("producer", ["empty", "issued", "landed"]), 1: ("mma-A", ["-", "-", "-", "soft_done", "dV,dQ,dK issued"]),
          2: ("softmax-g0", ["top", "bar", "s_full", "ldtm", "math", "arrived"]), 3: ("softmax-g1", ["top", "bar", "s_full", "ldtm", "math", "arrived"]),
          4: ("drain", ["top", "dq_full", "arrived", "staged"]),
-         5: ("mma-fine", ["looptop", "fenced", "elected", "dV+dQ", "dK", "dP(i+2)", "drainwait+fence"])}
+         5: ("mma-B", ["qdo_full", "dk_done", "drain_done", "dP,S issued"])}
 for i in range(4, 12):
     print(f"--- iteration {i}")
     for r, (name, tags) in roles.items():
