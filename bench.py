@@ -275,9 +275,14 @@ def main():
     n_l, mean_ms, tot_ms = ksum.get(key_ctx, (0, float("nan"), 0.0))
     flops = 2.0 * B * H * S * S * d
     achieved = flops / (mean_ms * 1e-3) / 1e12 if n_l else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, from the committed
+    # `ncu --set full` capture (profiles/r01_ncu_kernels.md, launches 0-2: 78.8 MB read + 18.7 MB written); the
+    # algorithmic bytes are q + k + v + out = 118 MB — q arrives L2-resident from the projection GEMM
+    traffic = 97.5e6 if (args.workload == "idefics2-8b" and args.layers is None) else None
     roofline = {"kernel": f"shifted_attn_fwd[{mimic_b200._lib.last_attn_impl()}] context pass (active=0, causal, S={S})",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+                "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_kernels.md (ncu --set full, same kernel and shape)" if traffic else None,
                 "peak_source": peaks["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops, "launches": n_l, "mean_ms": mean_ms,
                 "share_of_step": (tot_ms / n_eager) / (ms / args.steps) if n_l else None,

@@ -26,7 +26,10 @@ from .shift_model import ShiftModel
 
 class FlatShiftParams:
     def __init__(self, encoder, weight_decay: float, n_scalars: int = 4):
-        named = [(n, p) for n, p in encoder.named_parameters() if p.requires_grad and not n.startswith("lmm")]
+        # every trainable parameter reachable from the encoder: the shift parameters and — the backbone being a
+        # sub-module (`encoder.lmm`) — any LoRA adapter weights, like the reference's optimizer (src/shift_model.py:338-340)
+        named = [(n, p) for n, p in encoder.named_parameters() if p.requires_grad]
+        named.sort(key=lambda np_: np_[0].startswith("lmm"))      # stable: shift parameters first, adapters behind them
         if not named:
             raise AssertionError("No parameter to optimize.")
         dev = named[0][1].device

@@ -312,12 +312,94 @@ def gen_tiny_step():
     print("tiny step: loss", float(loss), "ce", float(ce), "mse", float(layer_loss["ffn_mse_loss"]))
 
 
+class _OracleLora(torch.nn.Module):
+    """LoRA on a frozen Linear as peft applies it (y = W x + (alpha / r) B A x; dropout 0 here), written out for the
+    oracle so the fixture does not depend on the product's mimic_b200.lora."""
+
+    def __init__(self, base, r, alpha, gen):
+        super().__init__()
+        self.base, self.scaling, self.enabled = base, alpha / r, True
+        self.A = torch.nn.Parameter(torch.randn(r, base.in_features, generator=gen) * 0.1)
+        self.B = torch.nn.Parameter(torch.randn(base.out_features, r, generator=gen) * 0.1)
+
+    def forward(self, x):
+        y = self.base(x)
+        return y + (x @ self.A.t() @ self.B.t()) * self.scaling if self.enabled else y
+
+
+def gen_tiny_step_lora():
+    """BASELINE config 4 in miniature: MimIC + LoRA (r = 1, alpha = 2) on every self_attn.o_proj, the context pass with the
+    adapters disabled (src/shift_model.py:225), through the reference's own hooks and loss methods."""
+    mb = ref_loader.load_model_base()
+    from torch import nn
+
+    class TinyLMM(mb.ModelBase):
+        def __init__(self, model):
+            nn.Module.__init__(self)
+            self.model = model
+            self.model_name = "llava-interleave-qwen-7b-hf"
+            self.config = model.config
+            self._trackers_dict = {}
+
+    wrap = tiny_qwen2()
+    g = torch.Generator().manual_seed(4321)
+    loras = {}
+    for li, layer in enumerate(wrap.language_model.model.layers):
+        lo = _OracleLora(layer.self_attn.o_proj, 1, 2.0, g)
+        layer.self_attn.o_proj = lo
+        loras[f"language_model.model.layers.{li}.self_attn.o_proj"] = lo
+    lmm = TinyLMM(wrap)
+    enc = ref_loader.make_ref_encoder(256, 4, 8, lmm=lmm)
+    g2 = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g2) * 0.05)
+        for lin in enc.log_Z1_lin:
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g2) * 0.1)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g2) * 0.5)
+    init = {k: v.detach().clone() for k, v in enc.state_dict().items() if not k.startswith("lmm")}
+    model, sm = make_ref_shift_model(enc)
+    full_ids, qa_ids = build_tiny_ids()
+    tok = _Tok()
+    hooks = enc.register_record_hooks()
+    inputs = {"input_ids": full_ids, "attention_mask": full_ids != tok.pad_token_id}
+    q_inputs = {"input_ids": qa_ids, "attention_mask": qa_ids != tok.pad_token_id}
+    for lo in loras.values():
+        lo.enabled = False                                    # with self.lmm.model.disable_adapter()
+    with torch.no_grad():
+        lmm.model(**inputs)
+    for lo in loras.values():
+        lo.enabled = True
+    prefix_hs = model.get_hidden_states(model.generate_label_mask(inputs, 1))
+    hooks.update(enc.register_shift_hooks())
+    logits = lmm.model(**q_inputs)["logits"]
+    keep = q_inputs["attention_mask"][:, 1:]
+    ce = F.cross_entropy(logits[:, :-1][keep].float(), qa_ids[:, 1:][keep])
+    shift_hs = model.get_hidden_states(q_inputs["attention_mask"] & (qa_ids != tok.bos_token_id))
+    model.remove_hooks(hooks)
+    layer_loss = model.calculate_layer_wise_loss(shift_hs, prefix_hs)
+    loss = 0.5 * ce + 1.0 * sum(layer_loss.values())
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    lora_params = {f"{n}.{ab}": getattr(lo, ab) for n, lo in loras.items() for ab in ("A", "B")}
+    grads = torch.autograd.grad(loss, list(params.values()) + list(lora_params.values()))
+    rec = {"full_ids": full_ids.numpy(), "qa_ids": qa_ids.numpy(), "loss": loss.detach().numpy(),
+           "ce_loss": ce.detach().numpy(), "ffn_mse_loss": layer_loss["ffn_mse_loss"].detach().numpy()}
+    for (n, p), gr in zip(list(params.items()) + list(lora_params.items()), grads):
+        rec["grad." + n] = gr.numpy()
+    for n, v in init.items():
+        rec["init." + n] = v.numpy()
+    for n, p in lora_params.items():
+        rec["lora." + n] = p.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_step_lora.npz"), **rec)
+    print("tiny step + LoRA: loss", float(loss.detach()), "ce", float(ce.detach()), "mse", float(layer_loss["ffn_mse_loss"].detach()))
+
+
 def main():
     assert ref_loader.available(), "reference tree not found; golden vectors can only be made where it is"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gen_attention()
     gen_loss_pieces()
+    gen_tiny_step_lora()
     gen_tiny_step()
 
 

@@ -50,6 +50,54 @@ def test_tiny_step_cos_sim_and_logits_kl_match_reference():
         assert rel(g, z["cosk.grad." + n]) < 5e-4, n
 
 
+def test_tiny_step_with_lora_matches_reference():
+    """BASELINE config 4 in miniature (MimIC + LoRA r=1 on self_attn.o_proj, context pass with adapters disabled):
+    losses, shift-parameter gradients and adapter gradients against the reference-made fixture, then the adapters
+    join the flat optimizer buffer of the on-device trainer."""
+    from oracle.gen_golden import _Tok, tiny_qwen2
+    from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy
+    from mimic_b200.lora import LoraLinear, apply_lora, lora_state_dict
+    from mimic_b200.trainer import FlatShiftParams
+    z = np.load(os.path.join(GOLDEN, "tiny_step_lora.npz"))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = tiny_qwen2().cuda()
+    names = apply_lora(model, r"language_model\.model\.layers\.\d+\.self_attn\.o_proj$", r=1, lora_alpha=2.0, lora_dropout=0.0)
+    assert len(names) == 4
+    with torch.no_grad():
+        for n in names:
+            m = model.get_submodule(n)
+            assert isinstance(m, LoraLinear) and not m.base_layer.weight.requires_grad
+            m.lora_A["default"].weight.copy_(torch.from_numpy(z[f"lora.{n}.A"]))
+            m.lora_B["default"].weight.copy_(torch.from_numpy(z[f"lora.{n}.B"]))
+    lmm = HookedModel(model, "llava-interleave-qwen-7b-hf", processor=types.SimpleNamespace(tokenizer=_Tok()))
+    enc = AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+                           "ShiftStrategy.RECORD_HIDDEN_STATES").cuda()
+    enc.load_state_dict({k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}, strict=False)
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0,
+                                data=types.SimpleNamespace(num_image_in_query=1))
+    sm = ShiftModel(cfg, enc, Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    full_ids, qa_ids = torch.from_numpy(z["full_ids"]).cuda(), torch.from_numpy(z["qa_ids"]).cuda()
+    loss_dict = sm.forward_inputs({"input_ids": full_ids}, {"input_ids": qa_ids})
+    assert abs(float(loss_dict["ce_loss"]) - float(z["ce_loss"])) < 2e-5 * float(z["ce_loss"])
+    assert abs(float(loss_dict["ffn_mse_loss"]) - float(z["ffn_mse_loss"])) < 1e-4 * float(z["ffn_mse_loss"])
+    assert abs(float(loss_dict["loss"]) - float(z["loss"])) < 2e-5 * float(z["loss"])
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad}
+    shift_names = [n for n in params if not n.startswith("lmm")]
+    lora_names = [n for n in params if n.startswith("lmm")]
+    assert len(lora_names) == 8                                   # A and B of four o_proj, reached through enc.lmm
+    grads = dict(zip(params, torch.autograd.grad(loss_dict["loss"], list(params.values()))))
+    for n in shift_names:
+        assert rel(grads[n], z["grad." + n]) < 2e-4, n
+    for n in names:
+        assert rel(grads[f"lmm.model.{n}.lora_A.default.weight"], z[f"grad.{n}.A"]) < 2e-4, n
+        assert rel(grads[f"lmm.model.{n}.lora_B.default.weight"], z[f"grad.{n}.B"]) < 2e-4, n
+    assert set(k.split(".lora_")[1][0] for k in lora_state_dict(model)) == {"A", "B"}
+    # the adapters are optimizer state like the shift parameters (src/shift_model.py:338-340)
+    flat = FlatShiftParams(enc, weight_decay=1e-3)
+    assert flat.numel == sum(p.numel() for p in params.values())
+    assert all(n in flat.views for n in lora_names)
+
+
 def test_tiny_step_matches_reference():
     from oracle.gen_golden import _Tok, tiny_qwen2
     from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy, ops

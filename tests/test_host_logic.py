@@ -198,3 +198,46 @@ def test_key_mask_from_4d():
     c, k = key_mask_from_4d(add, T, S)
     assert c and torch.equal(k, km)
     assert key_mask_from_4d(None, 1, S) == (False, None)
+
+
+def test_lora_wrapper_semantics_cpu():
+    """mimic_b200.lora on CPU tensors (plain torch modules, no kernel involved): peft's forward, names and
+    disable_adapter()."""
+    import torch
+    from torch import nn
+    from mimic_b200.lora import LoraLinear, apply_lora, lora_state_dict
+
+    class Blk(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attn = nn.Module()
+            self.self_attn.o_proj = nn.Linear(8, 8, bias=False)
+            self.self_attn.q_proj = nn.Linear(8, 8, bias=False)
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.ModuleList([Blk(), Blk()])
+
+    torch.manual_seed(0)
+    m = M()
+    names = apply_lora(m, r"layers\.\d+\.self_attn\.o_proj$", r=1, lora_alpha=2.0, lora_dropout=0.0)
+    assert names == ["layers.0.self_attn.o_proj", "layers.1.self_attn.o_proj"]
+    lo = m.layers[0].self_attn.o_proj
+    assert isinstance(lo, LoraLinear) and isinstance(m.layers[0].self_attn.q_proj, nn.Linear)
+    x = torch.randn(3, 8)
+    assert torch.equal(lo(x), lo.base_layer(x))                      # B starts at zero (peft init)
+    with torch.no_grad():
+        lo.lora_B["default"].weight.normal_()
+    want = lo.base_layer(x) + (x @ lo.lora_A["default"].weight.t() @ lo.lora_B["default"].weight.t()) * 2.0
+    assert torch.allclose(lo(x), want, atol=1e-6)
+    with m.disable_adapter():
+        assert torch.equal(lo(x), lo.base_layer(x))
+    assert torch.allclose(lo(x), want, atol=1e-6)
+    assert sorted(lora_state_dict(m)) == sorted(f"layers.{i}.self_attn.o_proj.lora_{ab}.default.weight"
+                                                for i in (0, 1) for ab in "AB")
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert all(".lora_" in n for n in trainable if "o_proj" in n) and not lo.base_layer.weight.requires_grad
+    import pytest
+    with pytest.raises(ValueError):
+        apply_lora(M(), r"no_such_module$")
