@@ -38,6 +38,10 @@ class DecoderConfig:
     _attn_implementation: str = "sdpa"
     use_sliding_window: bool = False
     sliding_window: Optional[int] = None
+    # Idefics v1 only: a gated cross-attention block in front of every `cross_layer_interval`-th decoder layer, keys /
+    # values from `image_hidden_states` [B, n_img * 64, vision_embed_dim] (HF IdeficsGatedCrossAttentionLayer)
+    cross_layer_interval: int = 0
+    vision_embed_dim: int = 1280
 
     def __post_init__(self):
         if self.head_dim is None:
@@ -51,7 +55,7 @@ PRESETS = {
                                              num_attention_heads=32, num_key_value_heads=8, vocab_size=32003)),
     "idefics-9b": ("idefics-9b", dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
                                       num_attention_heads=32, num_key_value_heads=32, vocab_size=32002,
-                                      rms_norm_eps=1e-6)),
+                                      rms_norm_eps=1e-6, cross_layer_interval=4, vision_embed_dim=1280)),
     "llava-interleave-7b": ("llava-interleave-qwen-7b-hf", dict(hidden_size=4096, intermediate_size=11008,
                                                                 num_hidden_layers=32, num_attention_heads=32,
                                                                 num_key_value_heads=32, vocab_size=152000,
@@ -148,21 +152,73 @@ class DecoderLayer(nn.Module):
         return x + self.mlp(self.post_attention_layernorm(x))
 
 
+class CrossAttention(nn.Module):
+    """Idefics v1 cross-attention (same IdeficsAttention class as self-attention in HF, `is_cross_attention=True`):
+    queries from the text stream, keys / values from the image features, no RoPE, no causal mask.  It lives at
+    `model.gated_cross_attn_layers.N.cross_attn`, which the reference's self-attention regex
+    (`model\\.layers\\.\\d+\\.self_attn$`, src/shift_encoder.py:107) does not match: MimIC leaves it untouched."""
+
+    def __init__(self, cfg: DecoderConfig):
+        super().__init__()
+        self.is_cross_attention = True
+        self.head_dim = cfg.head_dim
+        D, H, d = cfg.hidden_size, cfg.num_attention_heads, cfg.head_dim
+        self.q_proj = nn.Linear(D, H * d, bias=False)
+        self.k_proj = nn.Linear(cfg.vision_embed_dim, H * d, bias=False)
+        self.v_proj = nn.Linear(cfg.vision_embed_dim, H * d, bias=False)
+        self.o_proj = nn.Linear(H * d, D, bias=False)
+
+    def forward(self, hidden_states, key_value_states=None, attention_mask=None, **kwargs):
+        B, T, _ = hidden_states.shape
+        d = self.head_dim
+        q = self.q_proj(hidden_states).view(B, T, -1, d).transpose(1, 2)
+        k = self.k_proj(key_value_states).view(B, key_value_states.shape[1], -1, d).transpose(1, 2)
+        v = self.v_proj(key_value_states).view(B, key_value_states.shape[1], -1, d).transpose(1, 2)
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask)
+        return self.o_proj(out.transpose(1, 2).reshape(B, T, -1)), None
+
+
+class GatedCrossAttentionLayer(nn.Module):
+    """x + tanh(alpha_cross_attn) * cross_attn(LN(x), image) ; then + tanh(alpha_dense) * mlp(LN(x))."""
+
+    def __init__(self, cfg: DecoderConfig):
+        super().__init__()
+        self.cross_attn = CrossAttention(cfg)
+        self.mlp = MLP(cfg)
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.alpha_cross_attn = nn.Parameter(torch.zeros(1))
+        self.alpha_dense = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x, image_hidden_states, image_attention_mask=None):
+        a, _ = self.cross_attn(self.input_layernorm(x), key_value_states=image_hidden_states,
+                               attention_mask=image_attention_mask)
+        x = x + torch.tanh(self.alpha_cross_attn).to(x.dtype) * a
+        return x + torch.tanh(self.alpha_dense).to(x.dtype) * self.mlp(self.post_attention_layernorm(x))
+
+
 class TextModel(nn.Module):
     def __init__(self, cfg: DecoderConfig):
         super().__init__()
         self.config = cfg
         self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size)
         self.layers = nn.ModuleList(DecoderLayer(cfg, i) for i in range(cfg.num_hidden_layers))
+        if cfg.cross_layer_interval > 0:
+            n_cross = (cfg.num_hidden_layers + cfg.cross_layer_interval - 1) // cfg.cross_layer_interval
+            self.gated_cross_attn_layers = nn.ModuleList(GatedCrossAttentionLayer(cfg) for _ in range(n_cross))
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
 
-    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, position_ids=None):
+    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, position_ids=None,
+                image_hidden_states=None, image_attention_mask=None):
         x = self.embed_tokens(input_ids) if inputs_embeds is None else inputs_embeds
         B, T, _ = x.shape
         if position_ids is None:
             position_ids = torch.arange(T, device=x.device)[None].expand(B, T)
         pe = rope_cos_sin(position_ids, self.config.head_dim, self.config.rope_theta, x.dtype)
-        for layer in self.layers:
+        interval = self.config.cross_layer_interval
+        for i, layer in enumerate(self.layers):
+            if interval > 0 and i % interval == 0 and image_hidden_states is not None:
+                x = self.gated_cross_attn_layers[i // interval](x, image_hidden_states, image_attention_mask)
             x = layer(x, pe, attention_mask)
         return self.norm(x)
 
@@ -196,9 +252,10 @@ class SyntheticLM(nn.Module):
         return self._text[0]
 
     def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, position_ids=None,
-                logits_to_keep: int = 0, **kwargs):
+                logits_to_keep: int = 0, image_hidden_states=None, image_attention_mask=None, **kwargs):
         h = self.text(input_ids=input_ids, inputs_embeds=inputs_embeds, attention_mask=attention_mask,
-                      position_ids=position_ids)
+                      position_ids=position_ids, image_hidden_states=image_hidden_states,
+                      image_attention_mask=image_attention_mask)
         hk = h[:, -logits_to_keep:] if logits_to_keep else h          # HF semantics: 0 = all positions
         return {"logits": self.lm_head(hk), "last_hidden_state": h}
 
@@ -222,6 +279,8 @@ def build_synthetic(preset: str, *, dtype=torch.bfloat16, device="cuda", seed: i
                 p.normal_(0.0, cfg.initializer_range, generator=gen)
             elif "norm" in name:
                 p.fill_(1.0)
+            elif "alpha_" in name:
+                p.fill_(0.5)                                  # trained-like gate (HF initialises it at 0 = block switched off)
             else:
                 p.zero_()
     model.requires_grad_(False)

@@ -34,11 +34,13 @@ from typing import Optional, Tuple
 import torch
 
 
-def visibility(T: int, S: int, B: int, causal: bool, key_mask: Optional[torch.Tensor]) -> torch.Tensor:
+def visibility(T: int, S: int, B: int, causal: bool, key_mask: Optional[torch.Tensor], device=None) -> torch.Tensor:
     """Boolean [B,1,T,S] mask of visible keys (True = attend)."""
-    s = torch.arange(S)[None, None, None, :]
-    t = torch.arange(T)[None, None, :, None]
-    vis = torch.ones(B, 1, T, S, dtype=torch.bool)
+    if device is None and key_mask is not None:
+        device = key_mask.device
+    s = torch.arange(S, device=device)[None, None, None, :]
+    t = torch.arange(T, device=device)[None, None, :, None]
+    vis = torch.ones(B, 1, T, S, dtype=torch.bool, device=device)
     if causal:
         vis = vis & (s <= t + (S - T))
     if key_mask is not None:
@@ -112,7 +114,7 @@ def shifted_attention_fwd(q, k, v, attn_shift_l=None, w_l=None, b_l=None, *, cau
     if scale is None:
         scale = 1.0 / math.sqrt(d)
     kk, vv = repeat_kv(k, H // Hkv), repeat_kv(v, H // Hkv)
-    vis = visibility(T, S, B, causal, key_mask)
+    vis = visibility(T, S, B, causal, key_mask, device=q.device)
     sa, lse_c = masked_attention(q, kk, vv, vis, scale)
     sa_t = sa.transpose(1, 2)                          # [B,T,H,d]  (src/shift_encoder.py:367 / 458)
     res = {"sa": sa_t, "lse_c": lse_c}
@@ -140,7 +142,7 @@ def shifted_attention_bwd(q, k, v, attn_shift_l, w_l, b_l, d_out, *, causal=True
     if scale is None:
         scale = 1.0 / math.sqrt(d)
     kk, vv = repeat_kv(k, G), repeat_kv(v, G)
-    vis = visibility(T, S, B, causal, key_mask)
+    vis = visibility(T, S, B, causal, key_mask, device=q.device)
     s = torch.matmul(q, kk.transpose(-2, -1)) * scale                     # [B,H,T,S]
     sm = s.masked_fill(~vis, float("-inf"))
     lse_c = torch.logsumexp(sm, dim=-1)

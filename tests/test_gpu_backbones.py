@@ -1,0 +1,94 @@
+"""BASELINE configs 3 and 4 in miniature: the MimIC step on the Idefics-v1 layout (gated cross-attention blocks that
+the shift hooks must leave alone, image features entering by cross-attention) and on the LLaVA/Qwen2 layout (q/k/v
+bias, LoRA on o_proj).  The whole step through the CUDA kernels is compared with the same step where the fused
+attention op is replaced by the oracle's restatement of SDPA + do_shift (oracle/shifted_attention.py)."""
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+MIMIC = ("ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
+         "ShiftStrategy.RECORD_HIDDEN_STATES")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _step(preset, dtype, oracle_attention, lora=False, **cfg_over):
+    from oracle import shifted_attention as OA
+    from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy
+    from mimic_b200.backbone import build_synthetic, synthetic_batch, synthetic_processor
+    from mimic_b200.lora import apply_lora
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model, name = build_synthetic(preset, dtype=dtype, device="cuda", **cfg_over)
+    if lora:
+        torch.manual_seed(0)                                    # peft-style kaiming init of A draws from the global generator
+        apply_lora(model, r"language_model\.model\.layers\.\d+\.self_attn\.o_proj$", r=1, lora_alpha=2.0, lora_dropout=0.0)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if ".lora_B." in n:
+                    p.normal_(0.0, 0.1, generator=g)            # B = 0 would hide the adapter path
+    lmm = HookedModel(model, name, processor=synthetic_processor())
+    enc = AttnApproximator(lmm, *MIMIC).cuda()
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():                                       # trained-like shift parameters
+        enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.05)
+        for lin in enc.log_Z1_lin:
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.1)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.5)
+    if oracle_attention:
+        def fused(layer_idx, q, k, v, key_mask, causal, scale=None):
+            active = enc.attn_shift_handles[layer_idx].active
+            lin = enc.log_Z1_lin[layer_idx]
+            r = OA.shifted_attention_fwd(q.float(), k.float(), v.float(), enc.attn_shift[layer_idx], lin.weight, lin.bias,
+                                         causal=causal, key_mask=key_mask, scale=scale, active=active)
+            return r["out"].to(q.dtype)
+        enc.fused_attention = fused
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0, data=types.SimpleNamespace(num_image_in_query=1))
+    sm = ShiftModel(cfg, enc, Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    full, qa = synthetic_batch(2, 96, 24, model.config.vocab_size, seed=3, max_left_pad=5, device="cuda")
+    inputs, q_inputs = {"input_ids": full}, {"input_ids": qa}
+    if model.config.cross_layer_interval > 0:
+        gi = torch.Generator().manual_seed(7)
+        img = torch.randn(2, 4 * 8, model.config.vision_embed_dim, generator=gi).to("cuda", dtype)
+        inputs["image_hidden_states"] = img                     # 3 context images + the query image
+        q_inputs["image_hidden_states"] = img[:, -8:]           # the query image only
+    loss = sm.forward_inputs(inputs, q_inputs)
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad}
+    grads = dict(zip(params, torch.autograd.grad(loss["loss"], list(params.values()))))
+    return model, enc, {k: float(v) for k, v in loss.items()}, grads
+
+
+@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 4e-2)], ids=["fp32-d64", "bf16-d128"])
+def test_idefics_v1_layout_cross_attention_untouched(dtype, heads, tol):
+    from mimic_b200.backbone import CrossAttention
+    kw = dict(num_layers=5, hidden_size=256, intermediate_size=512, num_attention_heads=heads, num_key_value_heads=heads,
+              vocab_size=512, vision_embed_dim=64)
+    model, enc, loss, grads = _step("idefics-9b", dtype, False, **kw)
+    _, _, loss_o, grads_o = _step("idefics-9b", dtype, True, **kw)
+    # the shift hooks replaced the five self-attention forwards and none of the two cross-attention ones
+    assert all(type(l.self_attn).forward is not l.self_attn.forward.__func__ for l in model.model.layers)
+    assert all(g_.cross_attn.forward.__func__ is CrossAttention.forward for g_ in model.model.gated_cross_attn_layers)
+    assert len(enc.attn_shift_handles) == 5 and enc.attn_shift.shape[0] == 5
+    for k in ("loss", "ce_loss", "ffn_mse_loss"):
+        assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
+    for n in grads:
+        assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
+
+
+@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 4e-2)], ids=["fp32-d64", "bf16-d128"])
+def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
+    kw = dict(num_layers=3, hidden_size=256, intermediate_size=512, num_attention_heads=heads, num_key_value_heads=heads,
+              vocab_size=1000)
+    model, enc, loss, grads = _step("llava-interleave-7b", dtype, False, lora=True, **kw)
+    _, _, loss_o, grads_o = _step("llava-interleave-7b", dtype, True, lora=True, **kw)
+    assert model.language_model.model.layers[0].self_attn.q_proj.bias is not None
+    assert sum(1 for n in grads if ".lora_" in n) == 6
+    for k in ("loss", "ce_loss", "ffn_mse_loss"):
+        assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
+    for n in grads:
+        assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
