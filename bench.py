@@ -28,8 +28,12 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     "idefics2-8b": dict(preset="idefics2-8b", B=2, S_ctx=3200, T_q=128),
-    "idefics-9b": dict(preset="idefics-9b", B=2, S_ctx=1024, T_q=32),
-    "llava-interleave-7b": dict(preset="llava-interleave-7b", B=2, S_ctx=8192, T_q=768),
+    # BASELINE config 3: 32-shot Idefics-v1, 3 text tokens per image, pixels enter through the gated cross-attention
+    # blocks (stock PyTorch, untouched by MimIC): 33 x 64 image tokens in the context pass, 64 in the query pass
+    "idefics-9b": dict(preset="idefics-9b", B=2, S_ctx=1024, T_q=32, n_img_ctx=33, n_img_q=1),
+    # BASELINE config 4: MimIC + LoRA (r=1, alpha=2, dropout 0.05 on self_attn.o_proj: scripts/run_mimic_lora.sh)
+    "llava-interleave-7b": dict(preset="llava-interleave-7b", B=2, S_ctx=8192, T_q=768,
+                                lora=r"language_model\.model\.layers\.\d+\.self_attn\.o_proj$"),
     "tiny": dict(preset="tiny", B=2, S_ctx=512, T_q=64),
 }
 
@@ -164,6 +168,10 @@ def main():
 
     model, model_name = build_synthetic(wl["preset"], device=dev, num_layers=args.layers)
     cfgm = model.config
+    if wl.get("lora"):
+        from mimic_b200.lora import apply_lora
+        torch.manual_seed(3407)
+        apply_lora(model, wl["lora"], r=1, lora_alpha=2.0, lora_dropout=0.05)
     lmm = HookedModel(model, model_name, processor=synthetic_processor())
     enc = AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
                            "ShiftStrategy.RECORD_HIDDEN_STATES", attn_impl=args.attn_impl).to(dev)
@@ -176,6 +184,14 @@ def main():
     full_h, qa_h = synthetic_batch(B, S, T, cfgm.vocab_size, seed=3407 + rank)
     full_pin, qa_pin = full_h.pin_memory(), qa_h.pin_memory()
     full_d, qa_d = full_h.to(dev), qa_h.to(dev)
+    extra_ctx, extra_q = {}, {}
+    if wl.get("n_img_ctx"):                 # synthetic perceiver-resampler outputs (the vision tower is out of scope)
+        gi = torch.Generator(device=dev).manual_seed(3407 + rank)
+        img = torch.randn(B, wl["n_img_ctx"] * 64, cfgm.vision_embed_dim, device=dev, generator=gi).to(torch.bfloat16) * 0.02
+        extra_ctx = {"image_hidden_states": img}
+        extra_q = {"image_hidden_states": img[:, -wl["n_img_q"] * 64:].contiguous()}
+    pin_ctx = {k: v.cpu().pin_memory() for k, v in extra_ctx.items()}
+    pin_q = {k: v.cpu().pin_memory() for k, v in extra_q.items()}
 
     def finish():
         # a captured graph that holds NCCL kernels can stall process-group teardown: drop it first, then leave
@@ -191,21 +207,22 @@ def main():
     use_graph = not args.no_graph
 
     def step_eager():
-        trainer.micro_step({"input_ids": full_d}, {"input_ids": qa_d})
+        trainer.micro_step({"input_ids": full_d, **extra_ctx}, {"input_ids": qa_d, **extra_q})
 
     def step_resident():
         if use_graph:
-            trainer.graph_step([({"input_ids": full_d}, {"input_ids": qa_d})])
+            trainer.graph_step([({"input_ids": full_d, **extra_ctx}, {"input_ids": qa_d, **extra_q})])
         else:
             step_eager()
 
     def step_e2e():
         if use_graph:      # pinned host ids -> static device buffers (H2D inside the timed region) -> replay
-            trainer.graph_step([({"input_ids": full_pin}, {"input_ids": qa_pin})])
+            trainer.graph_step([({"input_ids": full_pin, **pin_ctx}, {"input_ids": qa_pin, **pin_q})])
         else:
             f = full_pin.to(dev, non_blocking=True)
             q = qa_pin.to(dev, non_blocking=True)
-            trainer.micro_step({"input_ids": f}, {"input_ids": q})
+            trainer.micro_step({"input_ids": f, **{k: v.to(dev, non_blocking=True) for k, v in pin_ctx.items()}},
+                               {"input_ids": q, **{k: v.to(dev, non_blocking=True) for k, v in pin_q.items()}})
         return trainer.logged_scalars()          # D2H read of the step's result
 
     def barrier():
@@ -241,7 +258,7 @@ def main():
     step_eager()
     launches_per_step = ops.launch_count - n0
     if use_graph:
-        trainer.capture({"input_ids": full_d}, {"input_ids": qa_d})
+        trainer.capture({"input_ids": full_d, **extra_ctx}, {"input_ids": qa_d, **extra_q})
     for _ in range(args.warmup):
         step_resident()
     if rank == 0:
@@ -306,7 +323,8 @@ def main():
                    "step_launch": "whole-step CUDA graph replay" if use_graph else "eager",
                    "eager_ms_per_step": ms_eager / n_eager,
                    "l2": "inputs larger than L2: every step streams the 14.5 GB frozen backbone"},
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": (full_pin.numel() + qa_pin.numel()) * 8,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": (full_pin.numel() + qa_pin.numel()) * 8 +
+                sum(v.numel() * v.element_size() for v in list(pin_ctx.values()) + list(pin_q.values())),
                 "d2h_bytes_per_step": 4 * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "own_kernels": own, "hbm_kernels": extra,
         "tokens_per_s_per_gpu": value / world, "losses": scal,
