@@ -92,3 +92,47 @@ def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
     for n in grads:
         assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
+
+
+def test_decode_with_kv_cache_matches_oracle():
+    """generation-time use of the replaced forward (eval.py:52-67): prefill, then q_len = 1 and 2 against
+    an HF KV cache with the shift active.  The cached flow through the CUDA kernels (T < S, causal offset S - T,
+    unmasked lse over the S cached keys) is compared with the same flow on the oracle's SDPA + do_shift."""
+    from transformers import DynamicCache
+    from oracle import shifted_attention as OA
+    from oracle.gen_golden import _Tok, tiny_qwen2
+    from mimic_b200 import AttnApproximator, HookedModel
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ids = torch.randint(3, 512, (2, 12), generator=torch.Generator().manual_seed(5)).cuda()
+    am = torch.ones(2, 12, dtype=torch.long, device="cuda")
+    am[1, :2] = 0                                               # a left-padded prompt
+    logits = {}
+    for which in ("cuda", "oracle"):
+        model = tiny_qwen2().cuda()
+        lmm = HookedModel(model, "llava-interleave-qwen-7b-hf", processor=types.SimpleNamespace(tokenizer=_Tok()))
+        enc = AttnApproximator(lmm, *MIMIC).cuda()
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.05)
+            for lin in enc.log_Z1_lin:
+                lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.1)
+                lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.5)
+        if which == "oracle":
+            def fused(layer_idx, q, k, v, key_mask, causal, scale=None, enc=enc):
+                lin = enc.log_Z1_lin[layer_idx]
+                r = OA.shifted_attention_fwd(q.float(), k.float(), v.float(), enc.attn_shift[layer_idx], lin.weight, lin.bias,
+                                             causal=causal, key_mask=key_mask, scale=scale,
+                                             active=enc.attn_shift_handles[layer_idx].active)
+                return r["out"].to(q.dtype)
+            enc.fused_attention = fused
+        enc.register_shift_hooks()
+        cache = DynamicCache(config=model.config)
+        outs = []
+        with torch.no_grad():
+            for a, b in ((0, 9), (9, 10), (10, 12)):            # prefill, one token, two tokens
+                o = model(input_ids=ids[:, a:b], attention_mask=am[:, :b], past_key_values=cache, use_cache=True)
+                outs.append(o["logits"])
+        assert cache.get_seq_length() == 12
+        logits[which] = outs
+    for a, b in zip(logits["cuda"], logits["oracle"]):
+        assert a.shape == b.shape and rel(a, b) < 1e-4
