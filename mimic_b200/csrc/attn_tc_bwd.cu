@@ -16,7 +16,8 @@
 //   drain warps: dQ^T TMEM -> registers -> fp32 smem [64][128] -> ONE bulk reduce-add
 //        (cp.reduce.async.bulk .add.f32) into the fp32 dq accumulator — no per-element atomics.
 // Delta' folds the visible part of the shift term: Delta' = g.SA + dz exp(lse_c - lse_full) (prep kernel).
-// TMEM map (512 cols): dV [0,128) dK [128,256) SdQ0 [256,320) SdQ1 [320,384) dP0 [384,448) dP1 [448,512).
+// TMEM map (512 cols): dV [0,128) dK [128,256) S0 [256,320) S1 [320,384) dP0 [384,448) dP1 [448,512).
+// S[st] holds S^T then P^T; dP[st] holds dP^T, then dS^T, then dQ^T (so S^T(i+2) only waits for dV(i), see the issuers).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -48,7 +49,7 @@ constexpr int OFF_K = 0, OFF_V = KV_TILE, OFF_Q = 2 * KV_TILE, OFF_DO = OFF_Q + 
               OFF_STAGE = OFF_DS + 2 * DS_TILE, OFF_STATS = OFF_STAGE + STAGE_BYTES, OFF_BAR = OFF_STATS + 4 * BQ * 16,
               OFF_TMEM = OFF_BAR + 24 * 8, SMEM_BYTES = OFF_TMEM + 16;
 
-enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, DK_DONE = 16, N_BARS = 18 };
+enum Bar { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 4, S_FULL = 7, SOFT_DONE = 9, DQ_FULL = 11, DRAIN_DONE = 13, DKV_FULL = 15, DV_DONE = 16, DP_FULL = 18, N_BARS = 20 };
 
 constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_SDQ = 256, TM_DP = 384;
 constexpr uint32_t IDESC_ST = idesc_bf16(128, BQ, 0, 0);     // S^T, dP^T : A, B K-major
@@ -116,7 +117,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_init(&bars[SOFT_DONE + i], 256);
         mbar_init(&bars[DQ_FULL + i], 1);
         mbar_init(&bars[DRAIN_DONE + i], 128);
-        mbar_init(&bars[DK_DONE + i], 1);
+        mbar_init(&bars[DV_DONE + i], 1);
+        mbar_init(&bars[DP_FULL + i], 1);
       }
       mbar_init(&bars[DKV_FULL], 1);
       fence_barrier_init();
@@ -170,12 +172,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1 || warp == 22) {
     // ===================== two MMA issuers =====================
-    // The single issuing warp was the bottleneck (instruction latency of one warp: ~8.7 cycles per instruction, ~350
-    // instructions per iteration).  The stream is split by operand, not by iteration, so each accumulator keeps ONE issuer:
-    //   warp 1  (A):  dV(i)  dQ^T(i) | commit DQ_FULL   dK(i) | commit DK_DONE[st], QDO_EMPTY        after SOFT_DONE(i)
-    //   warp 22 (B):  dP^T(i+2)  after DK_DONE(i)   (dK(i) has read dS^T(i) out of dP[st])
-    //                 S^T(i+2)   after DRAIN_DONE(i) (the drain warps emptied dQ^T(i) out of SdQ[st]) | commit S_FULL
-    // Every cross-issuer hazard is an explicit mbarrier; inside one issuer the tensor pipe runs in issue order.
+    // One issuing warp runs at ~8.7 cycles per instruction (~350 instructions per iteration): it was the bottleneck.
+    // The stream is split by operand so each accumulator keeps ONE issuer, and ordered so that the next S^T only
+    // waits for dV:
+    //   warp 1  (A), after SOFT_DONE(i):  dV(i) | commit DV_DONE[st]   dK(i)   dQ^T(i) -> dP[st] | commit DQ_FULL, QDO_EMPTY
+    //   warp 22 (B):  S^T(i+2) -> S[st]   after DV_DONE(i)   (dV(i) has read P^T(i))            | commit S_FULL[st]
+    //                 dP^T(i+2) -> dP[st] after DRAIN_DONE(i) (dQ^T(i) drained; dK(i) read dS^T) | commit DP_FULL[st]
+    // The softmax group starts its exponentials on S^T(i+2) while dK(i), dQ^T(i), the drain and dP^T(i+2) are still
+    // running.  Every cross-issuer hazard is an explicit mbarrier; inside one issuer the tensor pipe runs in issue order.
     // All 32 lanes run the control flow (waits, address arithmetic stay warp-uniform); one elected lane issues.
     if (n > 0) {
       constexpr uint32_t HI = desc_hi_sw128(1024);
@@ -195,24 +199,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t prev_par = ((i2 >> 1) & 1) ^ 1;       // parity of the phase completed by iteration i2 - 2 (passes for i2 < 2)
           mbar_wait(&bars[QDO_FULL + qs2], qph2, 210 + qs2);
           if (lane == 0) stamp(5, i2, 0);
-          if (nc2) {
-            mbar_wait(&bars[DK_DONE + st2], prev_par, 212 + st2);
-            if (lane == 0) stamp(5, i2, 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t do_km = do_km0 + qs2 * (Q_TILE >> 4), d_p = tmem_base + TM_DP + st2 * BQ;
-#pragma unroll
-              for (int k = 0; k < HD / 16; ++k) {
-                const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
-                if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-                else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
-              }
-            }
-            __syncwarp();
-          }
-          if (!dbg(2)) mbar_wait(&bars[DRAIN_DONE + st2], prev_par, 215 + st2);
-          if (!nc2) mbar_wait(&bars[DK_DONE + st2], prev_par, 213 + st2);   // S_FULL below also frees dP[st2] for the softmax group
-          if (lane == 0) stamp(5, i2, 2);
+          mbar_wait(&bars[DV_DONE + st2], prev_par, 212 + st2);
+          if (lane == 0) stamp(5, i2, 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t q_km = q_km0 + qs2 * (Q_TILE >> 4), d_s = tmem_base + TM_SDQ + st2 * BQ;
@@ -225,6 +213,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tc_commit(&bars[S_FULL + st2]);
           }
           __syncwarp();
+          if (!dbg(2)) mbar_wait(&bars[DRAIN_DONE + st2], prev_par, 215 + st2);
+          if (lane == 0) stamp(5, i2, 2);
+          tc_fence_after();
+          if (elect_one()) {
+            if (nc2) {
+              const uint32_t do_km = do_km0 + qs2 * (Q_TILE >> 4), d_p = tmem_base + TM_DP + st2 * BQ;
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t ko_kv = ((k >> 2) * KV_HALF + (k & 3) * 32) >> 4, ko_q = ((k >> 2) * Q_HALF + (k & 3) * 32) >> 4;
+                if (k == 0) mma_ss_c<false>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+                else mma_ss_c<true>(d_p, desc64(HI, v_km + ko_kv), desc64(HI, do_km + ko_q), IDESC_ST);
+              }
+            }
+            tc_commit(&bars[DP_FULL + st2]);                   // without MMAs in between: dP[st2] is simply free for dS^T
+          }
+          __syncwarp();
           if (lane == 0) stamp(5, i2, 3);
           qt2 = next_qt(qt2);
           if (++qs2 == NQS) {
@@ -233,7 +237,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
       } else {
-        // ---------------- issuer A: dV / dQ^T / dK of iteration i ----------------
+        // ---------------- issuer A: dV / dK / dQ^T of iteration i ----------------
         int qt_i = qt_first, qs = 0;
         bool dv_started = false;
         for (int i = 0; i < n; ++i) {
@@ -252,18 +256,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               for (int k = 0; k < BQ / 16; ++k)
                 mma_ts(tmem_base + TM_DV, a_p + 16 * k, desc64(HI, do_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || dv_started) ? 1u : 0u);
             }
-            // dQ^T = K^T dS^T : K = 16 keys per step; overwrites P^T(i) in SdQ[st] (dV(i) has read it: pipe order)
-#pragma unroll
-            for (int k = 0; k < BN / 16; ++k) {
-              if (k == 0) mma_ss_c<false>(a_p, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
-              else mma_ss_c<true>(a_p, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
-            }
-            tc_commit(&bars[DQ_FULL + st]);
-            // dK += dS^T Q_i
+            tc_commit(&bars[DV_DONE + st]);                    // S[st] may take S^T(i+2)
+            // dK += dS^T Q_i   (A operand: dS^T in dP[st])
 #pragma unroll
             for (int k = 0; k < BQ / 16; ++k)
               mma_ts(tmem_base + TM_DK, a_ds + 16 * k, desc64(HI, q_mn + k * (2048 >> 4)), IDESC_DKV, (k > 0 || i > 0) ? 1u : 0u);
-            tc_commit(&bars[DK_DONE + st]);
+            // dQ^T = K^T dS^T : K = 16 keys per step, B from shared memory; lands in dP[st] over dS^T(i) (dK(i) has read it)
+#pragma unroll
+            for (int k = 0; k < BN / 16; ++k) {
+              if (k == 0) mma_ss_c<false>(a_ds, desc64(HI, k_mn), desc64(HI, ds_mn), IDESC_DQT);
+              else mma_ss_c<true>(a_ds, desc64(HI, k_mn + k * (2048 >> 4)), desc64(HI, ds_mn + k * (2048 >> 4)), IDESC_DQT);
+            }
+            tc_commit(&bars[DQ_FULL + st]);
             tc_commit(&bars[QDO_EMPTY + qs]);
           }
           __syncwarp();
@@ -338,66 +342,108 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (srole >= 0) stamp(srole, i, 2);
       tc_fence_after();
       uint8_t* ds_row = sDS + st * DS_TILE + r * 128;
+      // ---- phase 1 (needs S^T only): val = P for visible entries, -dz exp2(s - lse_full) for excluded ones, packed bf16.
+      // P^T goes to TMEM (A operand of dV); val stays in registers for phase 2.
+      uint32_t val[2][8];
+      uint32_t vws[2], xws[2];
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int cq = 2 * hf + pass;                    // 16-column group of the 64-wide tile
         const uint32_t t_s = tmem_base + lane_off + TM_SDQ + st * BQ + 16 * cq;
-        const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ + 16 * cq;
         const float4* stt = gstats + sb * BQ + 16 * cq;
         // visibility of queries t0+16*cq+c (c = 0..15) for key s: visible iff s <= t + off
         const uint32_t trow = low_bits_b(T - t0 - 16 * cq) & 0xFFFFu;
         const uint32_t cz = (p.causal ? ~low_bits_b(s - off - t0 - 16 * cq) : 0xFFFFFFFFu) & 0xFFFFu;
         const uint32_t vw = key_ok ? (trow & cz) : 0u;
         const uint32_t xw = (p.active && key_in) ? (trow & ~vw) : 0u;
-        float sv[16], dpv[16];
+        vws[pass] = vw;
+        xws[pass] = xw;
+        float sv[16];
         tmem_ld16(t_s, sv);
-        if (nc) tmem_ld16(t_dp, dpv);
         tc_wait_ld();
         if (srole >= 0 && pass == 0) stamp(srole, i, 3);
-        uint32_t pk[8], dk_[8];
         const bool all_v = __all_sync(0xffffffffu, vw == 0xFFFFu);
         const bool all_x = __all_sync(0xffffffffu, vw == 0u && xw == 0xFFFFu);
-        if (all_v && nc) {
-          // interior causal tile: every entry visible.  dS (unscaled) = P (dP - Delta'); scale is applied to dK / dQ later
+        if (all_v) {
 #pragma unroll
           for (int c2 = 0; c2 < 8; ++c2) {
             const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
-            const float p0 = ex2(fmaf(sv[2 * c2], scale2, a.x)), p1 = ex2(fmaf(sv[2 * c2 + 1], scale2, bq.x));
-            pk[c2] = pack_bf16(p0, p1);
-            dk_[c2] = pack_bf16(p0 * (dpv[2 * c2] - a.y), p1 * (dpv[2 * c2 + 1] - bq.y));
+            val[pass][c2] = pack_bf16(ex2(fmaf(sv[2 * c2], scale2, a.x)), ex2(fmaf(sv[2 * c2 + 1], scale2, bq.x)));
           }
+          if (nc) tmem_st8(t_s, val[pass]);
         } else if (all_x) {
-          // tile above the diagonal (shift term only): dS = -dz exp2(s - lse_full)
 #pragma unroll
           for (int c2 = 0; c2 < 8; ++c2) {
             const float4 a = stt[2 * c2], bq = stt[2 * c2 + 1];
-            pk[c2] = 0u;
-            dk_[c2] = pack_bf16(a.z * ex2(fmaf(sv[2 * c2], scale2, a.w)), bq.z * ex2(fmaf(sv[2 * c2 + 1], scale2, bq.w)));
+            val[pass][c2] = pack_bf16(a.z * ex2(fmaf(sv[2 * c2], scale2, a.w)), bq.z * ex2(fmaf(sv[2 * c2 + 1], scale2, bq.w)));
+          }
+          if (nc) {
+            const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(t_s, zero);
           }
         } else {
+          uint32_t pk[8];
 #pragma unroll
           for (int c2 = 0; c2 < 8; ++c2) {
-            float pv[2], dsv[2];
+            float ve[2], pe[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int c = 2 * c2 + e;
               const float4 stc = stt[c];
-              float pe = 0.f, de = 0.f;
+              ve[e] = 0.f;
+              pe[e] = 0.f;
               if ((vw >> c) & 1u) {
-                pe = ex2(fmaf(sv[c], scale2, stc.x));
-                de = pe * ((nc ? dpv[c] : 0.f) - stc.y);
+                pe[e] = ex2(fmaf(sv[c], scale2, stc.x));
+                ve[e] = pe[e];
               } else if ((xw >> c) & 1u) {
-                de = stc.z * ex2(fmaf(sv[c], scale2, stc.w));
+                ve[e] = stc.z * ex2(fmaf(sv[c], scale2, stc.w));
               }
-              pv[e] = pe;
-              dsv[e] = de;
             }
-            pk[c2] = pack_bf16(pv[0], pv[1]);
-            dk_[c2] = pack_bf16(dsv[0], dsv[1]);
+            val[pass][c2] = pack_bf16(ve[0], ve[1]);
+            pk[c2] = pack_bf16(pe[0], pe[1]);
           }
+          if (nc) tmem_st8(t_s, pk);
         }
-        if (srole >= 0 && pass == 1) stamp(srole, i, 4);
-        if (nc) tmem_st8(t_s, pk);                              // P^T  (A operand of dV): packed cols [16cq, 16cq+8)
+      }
+      if (srole >= 0) stamp(srole, i, 4);
+      // ---- phase 2 (needs dP^T; dP[st] is free for dS^T once DP_FULL fired): dS = P (dP - Delta') on visible entries
+      mbar_wait(&bars[DP_FULL + st], (i >> 1) & 1, 312 + st);
+      tc_fence_after();
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int cq = 2 * hf + pass;
+        const uint32_t t_dp = tmem_base + lane_off + TM_DP + st * BQ + 16 * cq;
+        const float4* stt = gstats + sb * BQ + 16 * cq;
+        const uint32_t vw = vws[pass], xw = xws[pass];
+        uint32_t dk_[8];
+        const bool any_v = __any_sync(0xffffffffu, vw != 0u);
+        if (any_v && nc) {
+          float dpv[16];
+          tmem_ld16(t_dp, dpv);
+          tc_wait_ld();
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2) {
+            // unpack bf16 pair: low half = element 2 c2, high half = element 2 c2 + 1
+            const float v0 = __uint_as_float(val[pass][c2] << 16), v1 = __uint_as_float(val[pass][c2] & 0xFFFF0000u);
+            const float d0 = ((vw >> (2 * c2)) & 1u) ? v0 * (dpv[2 * c2] - stt[2 * c2].y) : v0;
+            const float d1 = ((vw >> (2 * c2 + 1)) & 1u) ? v1 * (dpv[2 * c2 + 1] - stt[2 * c2 + 1].y) : v1;
+            dk_[c2] = pack_bf16(d0, d1);
+          }
+        } else if (any_v) {
+          // visible entries of a tile without dP^T (cannot happen for causal tiles: nc covers every tile with a visible
+          // entry; kept for non-causal edge shapes): dS = -P Delta'
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2) {
+            const float v0 = __uint_as_float(val[pass][c2] << 16), v1 = __uint_as_float(val[pass][c2] & 0xFFFF0000u);
+            const float d0 = ((vw >> (2 * c2)) & 1u) ? -v0 * stt[2 * c2].y : v0;
+            const float d1 = ((vw >> (2 * c2 + 1)) & 1u) ? -v1 * stt[2 * c2 + 1].y : v1;
+            dk_[c2] = pack_bf16(d0, d1);
+          }
+        } else {
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2) dk_[c2] = val[pass][c2];
+        }
+        (void)xw;
         tmem_st8(t_dp, dk_);                                    // dS^T (A operand of dK)
         // dS^T row to smem: 16 queries = 32 B = two 16-byte chunks, 128B-swizzled by key row
 #pragma unroll
@@ -466,11 +512,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (dtr) stamp(4, i, 1);
       tc_fence_after();
       float v0[32], v1[32];
-      tmem_ld32(tmem_base + lane_off + TM_SDQ + st * BQ, v0);
-      tmem_ld32(tmem_base + lane_off + TM_SDQ + st * BQ + 32, v1);
+      tmem_ld32(tmem_base + lane_off + TM_DP + st * BQ, v0);
+      tmem_ld32(tmem_base + lane_off + TM_DP + st * BQ + 32, v1);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&bars[DRAIN_DONE + st]);              // TMEM buffer may be overwritten by S^T(i+2)
+      mbar_arrive(&bars[DRAIN_DONE + st]);              // dP[st] may take dP^T(i+2) / dS^T(i+2)
       if (dtr) stamp(4, i, 2);
       if (dbg(256)) continue;
       const int rows = min(BQ, T - qt * BQ);

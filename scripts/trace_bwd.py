@@ -21,9 +21,9 @@ _lib.lib.mimic_debug_set_trace(None, 0)
 t = buf.cpu().view(24, 8, 8)
 t0 = int(t[t > 0].min())
 roles = {0: ("producer", ["empty", "issued", "landed"]), 1: ("mma-A", ["-", "-", "-", "soft_done", "dV,dQ,dK issued"]),
-         2: ("softmax-g0", ["top", "bar", "s_full", "ldtm", "math", "arrived"]), 3: ("softmax-g1", ["top", "bar", "s_full", "ldtm", "math", "arrived"]),
+         2: ("softmax-g0", ["top", "bar", "s_full", "ldtm", "phase1", "arrived"]), 3: ("softmax-g1", ["top", "bar", "s_full", "ldtm", "phase1", "arrived"]),
          4: ("drain", ["top", "dq_full", "arrived", "staged"]),
-         5: ("mma-B", ["qdo_full", "dk_done", "drain_done", "dP,S issued"])}
+         5: ("mma-B", ["qdo_full", "dv_done", "S issued/drain_done", "dP issued"])}
 for i in range(4, 12):
     print(f"--- iteration {i}")
     for r, (name, tags) in roles.items():
