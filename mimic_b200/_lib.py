@@ -72,9 +72,11 @@ def _load() -> C.CDLL:
     import fcntl
     from . import build as _build
     try:
-        with open(LIB_PATH + ".lock", "w") as lock:      # ranks of one job import at the same time: one builds, the rest wait
-            fcntl.flock(lock, fcntl.LOCK_EX)
-            _build.build()            # no-op when the library is newer than csrc/ and include/; needs nvcc otherwise
+        if not _build.up_to_date():   # content hash of csrc/ + include/ against the one recorded at build time
+            with open(LIB_PATH + ".lock", "w") as lock:  # ranks of one job import at the same time: one builds, the rest wait
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                if not _build.up_to_date():
+                    _build.build(force=True)             # needs nvcc
     except RuntimeError:
         if not os.path.exists(LIB_PATH):
             raise                     # no library and no way to build it: fail loudly, there is no fallback path

@@ -27,6 +27,35 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libmimic_b200.so cannot be built")
 
 
+def _digest(paths) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for pth in sorted(paths):
+        h.update(os.path.basename(pth).encode())
+        with open(pth, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def sources_digest() -> str:
+    """Content hash of everything the library is built from (modification times do not survive a repo snapshot)."""
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "mimic_b200.h"))
+    return _digest(files)
+
+
+STAMP = LIB + ".sha256"        # next to the library: it travels with it (the object directory does not)
+
+
+def up_to_date() -> bool:
+    """True when libmimic_b200.so was built from exactly the sources now in the tree."""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == sources_digest()
+    except OSError:
+        return False
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -66,6 +95,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(STAMP, "w") as f:
+        f.write(sources_digest() + "\n")
     return LIB
 
 
