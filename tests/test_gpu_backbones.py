@@ -17,7 +17,7 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _step(preset, dtype, oracle_attention, lora=False, **cfg_over):
+def _step(preset, dtype, oracle_attention, lora=False, strategies=None, **cfg_over):
     from oracle import shifted_attention as OA
     from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy
     from mimic_b200.backbone import build_synthetic, synthetic_batch, synthetic_processor
@@ -33,7 +33,7 @@ def _step(preset, dtype, oracle_attention, lora=False, **cfg_over):
                 if ".lora_B." in n:
                     p.normal_(0.0, 0.1, generator=g)            # B = 0 would hide the adapter path
     lmm = HookedModel(model, name, processor=synthetic_processor())
-    enc = AttnApproximator(lmm, *MIMIC).cuda()
+    enc = AttnApproximator(lmm, *(strategies or MIMIC)).cuda()
     g = torch.Generator().manual_seed(11)
     with torch.no_grad():                                       # trained-like shift parameters
         enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.05)
@@ -92,6 +92,20 @@ def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
     for n in grads:
         assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
+
+
+def test_attn_record_point_config():
+    """src/config/encoder/mimic_attn_mse.yaml: the record point is the attention module output (RECORD_HIDDEN_STATES in the
+    attn strategy, ffn strategy null) -> loss key attn_mse_loss, same parity bar."""
+    strategies = (MIMIC[0] + " | ShiftStrategy.RECORD_HIDDEN_STATES", None)
+    kw = dict(num_layers=3, hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2, vocab_size=512)
+    _, enc, loss, grads = _step("idefics2-8b", torch.float32, False, strategies=strategies, **kw)
+    _, _, loss_o, grads_o = _step("idefics2-8b", torch.float32, True, strategies=strategies, **kw)
+    assert set(loss) == {"loss", "ce_loss", "attn_mse_loss"} and hasattr(enc, "attn_hidden_states") and not hasattr(enc, "ffn_hidden_states")
+    for k in loss:
+        assert abs(loss[k] - loss_o[k]) < 2e-4 * abs(loss_o[k]) + 1e-7, k
+    for n in grads:
+        assert rel(grads[n], grads_o[n]) < 2e-4, n
 
 
 def test_decode_with_kv_cache_matches_oracle():
