@@ -447,12 +447,23 @@ bool supports(const AttnParams& p, bool backward) {
 
 int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query tiles per CTA
 int fwd64(const AttnParams& p, cudaStream_t st);  // attn_tc_fwd64.cu: 64-key tiles, two CTAs per SM
+int fwd64p(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64p.cu: the same pipeline in persistent CTAs (static work lists)
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
-  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3": single-tile / ping-pong / 64-key two-CTA kernel
+  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3" / "4": single-tile / ping-pong / 64-key two-CTA (auto persistent) / persistent forced
   const int kern = force ? atoi(force) : 3;             // measured on B200: 3 is the fastest at every T
-  if (kern == 3 && (size_t)((p.S + 63) / 64) * 8 < 16000) return fwd64(p, st);
+  if ((kern == 3 || kern == 4) && (size_t)((p.S + 63) / 64) * 8 < 16000) {
+    // persistent variant: inactive handle (context pass), several tiles per CTA slot, AND the K/V of every (kv head,
+    // batch) stream fit L2 together — its CTAs in flight touch all streams at once.  Measured: +8 % (+16 % with a padding
+    // mask) at the Idefics2 context pass; -2 % with the shift active (equal work per tile, per-item tables); -17 % at
+    // T = 8192 with 64 MHA streams (268 MB of K/V)
+    const long long items = (long long)((p.T + 127) / 128) * p.H * p.B;
+    const long long kv_bytes = 2LL * p.B * p.Hkv * p.S * p.d * 2;
+    const bool persistent = kern == 4 || (!p.active && items >= 4LL * 2 * 148 && kv_bytes <= (48LL << 20));
+    if (persistent && !getenv("MIMIC_NO_PERSISTENT")) return fwd64p(p, st);
+    return fwd64(p, st);
+  }
   if (kern == 2 && p.T > BM) return fwd2(p, st);
   AttnParams pd = p;
   if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pd.debug_flags = atoi(e);

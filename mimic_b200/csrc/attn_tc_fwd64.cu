@@ -38,9 +38,11 @@ inline size_t smem_bytes(int S) { return OFF_KBITS + (size_t)((S + BN - 1) / BN)
 
 __device__ __forceinline__ uint32_t low_bits3(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
+// DBG = true: instrumented twin (timeline stamps of CTA 0 into p.trace, scripts/trace_fwd.py); compiled out otherwise.
+template <bool DBG>
 __global__ void __launch_bounds__(f64::THREADS, 2)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                     const __grid_constant__ CUtensorMap tm_v, AttnParams p) {
+                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, AttnParams p) {
   using namespace f64;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -57,6 +59,16 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + OFF_KBITS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the LAST CTA of the grid: a first-wave CTA pays cold instruction-cache misses on every code path (measured: 8700
+  // cycles for an epilogue that takes ~1500 warm) and says nothing about the steady state
+  const bool tracing = DBG && p.trace != nullptr && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 &&
+                       blockIdx.z == gridDim.z - 1;
+  auto stamp = [&](int role, int e) {                  // role r, event e -> trace[r * 8 + e]
+    if constexpr (DBG) {
+      if (tracing) p.trace[role * 8 + e] = clock64();
+    }
+  };
+  if (threadIdx.x == 0) stamp(0, 0);                   // CTA entry
   const int qt = gridDim.x - 1 - blockIdx.x;          // heaviest (latest) query tiles first
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.H / p.Hkv);
@@ -108,17 +120,28 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       w_s[st] = p.w[h * HD + st];
       shift_s[st] = p.shift[h * HD + st];
     }
+    // key-validity bits, one 32-key word per (warp, u): up to 16 independent byte loads in flight per lane — as a
+    // dependent load -> ballot chain this table cost ~6 us per CTA at S = 3200 with a padding mask
     const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * S : nullptr;
-    for (int wi = warp - 2; wi < n_tiles * 2; wi += 4) {
-      const int s = wi * 32 + lane;
-      const bool ok = s < S && (km == nullptr || km[s] != 0);
-      const uint32_t word = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) kbits[wi] = word;
+    for (int w0 = warp - 2; w0 < n_tiles * 2; w0 += 4 * 16) {
+      uint8_t ok[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int s = (w0 + 4 * u) * 32 + lane;
+        ok[u] = (s < S) ? (km == nullptr ? (uint8_t)1 : km[s]) : (uint8_t)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int wi = w0 + 4 * u;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok[u] != 0);
+        if (lane == 0 && wi < n_tiles * 2) kbits[wi] = word;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) stamp(0, 1);                   // prologue done
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + TM_O;
 
@@ -208,7 +231,9 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const float scale2 = p.scale * LOG2E;
 
     float z1 = 0.f;
+    const bool str = warp == 2 && lane == 0;
     mbar_wait(&bars[Q_FULL], 0, 300);
+    if (str) stamp(2, 0);                               // Q landed
     if (p.active) {
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf)
@@ -231,6 +256,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int j = 0; j < n; ++j) {
       const int st = j & 1;
       mbar_wait(&bars[S_FULL + st], (j >> 1) & 1, 310 + st);
+      if (str && j == 0) stamp(2, 1);                   // first score tile
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + st * BN;
       const int key0 = j * BN;
@@ -347,7 +373,9 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
+      if (str && j == 0) stamp(2, 2);                   // first softmax done
     }
+    if (str) stamp(2, 3);                               // all steps done
 
     // ---- epilogue ----
     const float inv = l_c > 0.f ? 1.f / l_c : 0.f;
@@ -363,7 +391,10 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(&bars[O_FULL], 0, 330);
       tc_fence_after();
     }
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_sb + (int64_t)t * p.o_st + (int64_t)h * p.o_sh;
+    if (str) stamp(2, 4);                               // O complete
+    // The output tile goes through shared memory (the Q tile is dead once O_FULL fired: every QK^T MMA has completed)
+    // and leaves with two TMA tile stores.  Thread-per-row global stores touch 32 different 128-byte lines per warp
+    // instruction (rows are H*d*2 bytes apart): ~2000 sector writes, ~3000 cycles of every CTA's tail.
 #pragma unroll
     for (int i2 = 0; i2 < 2; ++i2) {                     // two 64-column halves: both TMEM loads in flight before the wait
       float o[64];
@@ -375,18 +406,28 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 64; ++c) o[c] = 0.f;
       }
-      if (row_ok) {
+      uint8_t* srow = sQ + i2 * Q_HALF + r * 128;        // 128B-swizzled [128 rows][64 cols] box, as the TMA map expects
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float f[8];
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = 64 * i2 + 8 * c8 + e;
-            f[e] = o[8 * c8 + e] * inv + (p.active ? mu * shift_s[c] : 0.f);
-          }
-          store8(orow + 64 * i2 + 8 * c8, f);
+        for (int e = 0; e < 4; ++e) {
+          const int c = 64 * i2 + 8 * c8 + 2 * e;
+          const float f0 = o[8 * c8 + 2 * e] * inv + (p.active ? mu * shift_s[c] : 0.f);
+          const float f1 = o[8 * c8 + 2 * e + 1] * inv + (p.active ? mu * shift_s[c + 1] : 0.f);
+          pk[e] = pack_bf16(f0, f1);
         }
+        *reinterpret_cast<uint4*>(srow + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+    }
+    fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+      tma_store_4d(&tm_o, sQ, 0, t0, h, b);
+      tma_store_4d(&tm_o, sQ + Q_HALF, 64, t0, h, b);
+      bulk_commit();
+      bulk_wait_read0();                                 // shared memory may be released (CTA exit) once the reads are done
+      stamp(2, 5);                                       // output tile handed to the TMA
     }
     if (row_ok) {
       const int64_t ridx = ((int64_t)b * p.H + h) * T + t;
@@ -402,24 +443,30 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+    if (lane == 0) stamp(0, 2);                          // CTA exit
   }
 }
 
 int fwd64(const AttnParams& p, cudaStream_t st) {
   using namespace f64;
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   int rc;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BM))) return rc;
+  if ((rc = make_map(&to, p.out, p.B, p.H, p.T, p.o_sb, p.o_sh, p.o_st, BM))) return rc;
   if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
   if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, BN))) return rc;
   const size_t smem = smem_bytes(p.S);
   static size_t configured = 0;
   if (smem > configured) {
-    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid((p.T + BM - 1) / BM, p.H, p.B);
-  attn_fwd_tc64_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, p);
+  AttnParams pp = p;
+  pp.trace = debug_trace_capacity() >= 64 ? debug_trace_buffer() : nullptr;
+  if (pp.trace != nullptr) attn_fwd_tc64_kernel<true><<<grid, THREADS, smem, st>>>(tq, tk, tv, to, pp);
+  else attn_fwd_tc64_kernel<false><<<grid, THREADS, smem, st>>>(tq, tk, tv, to, pp);
   MIMIC_LAUNCH_OK("attn_fwd_tc64_kernel");
   return MIMIC_OK;
 }

@@ -105,25 +105,29 @@ def bperf(B, H, Hkv, T, active, reps=5):
         print(f"bwd perf {impl} B={B} H={H} T={T} active={int(active)}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (prep+main+convert)", flush=True)
 
 
-def perf(B, H, Hkv, T, active, reps=10):
+def perf(B, H, Hkv, T, active, reps=10, mask=False):
     d = 128
+    km = None
+    if mask:
+        km = torch.ones(B, T, dtype=torch.bool, device="cuda")
+        km[B - 1, :13] = False
     q = torch.randn(B, H, T, d, device="cuda").bfloat16()
     k = torch.randn(B, Hkv, T, d, device="cuda").bfloat16()
     v = torch.randn(B, Hkv, T, d, device="cuda").bfloat16()
     sh, ww, bb = (torch.randn(H, d, device="cuda") * 0.5, torch.randn(H, d, device="cuda") * 0.2, torch.randn(H, device="cuda")) if active else (None,) * 3
     for impl in ("tcgen05",):
         for _ in range(3):
-            ops.shifted_attention_forward(q, k, v, None, sh, ww, bb, causal=True, active=active, scale=d ** -0.5, impl=impl)
+            ops.shifted_attention_forward(q, k, v, km, sh, ww, bb, causal=True, active=active, scale=d ** -0.5, impl=impl)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            ops.shifted_attention_forward(q, k, v, None, sh, ww, bb, causal=True, active=active, scale=d ** -0.5, impl=impl)
+            ops.shifted_attention_forward(q, k, v, km, sh, ww, bb, causal=True, active=active, scale=d ** -0.5, impl=impl)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         fl = (3 if active else 2) * B * H * T * T * d
-        print(f"perf {impl} B={B} H={H} T={T} active={int(active)}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        print(f"perf {impl} B={B} H={H} T={T} active={int(active)} mask={int(mask)}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
@@ -158,6 +162,7 @@ if __name__ == "__main__":
         bperf(4, 32, 32, 4096, True)
     if which in ("all", "perf"):
         perf(2, 32, 8, 3200, False)
+        perf(2, 32, 8, 3200, False, mask=True)
         perf(2, 32, 8, 3200, True)
         perf(4, 32, 32, 4096, False)
         perf(4, 32, 32, 4096, True)
