@@ -64,7 +64,8 @@ __device__ __forceinline__ uint32_t low_bits_b(int n) { return n >= 32 ? 0xFFFFF
 template <bool DBG>
 __global__ void __launch_bounds__(bw::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, AttnParams p) {
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv, AttnParams p) {
   using namespace bw;
   // address the dynamic window directly (no pointer rounding through integers): keeps every access LDS/STS
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -467,10 +468,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
     }
     {
-      const int which = g;                               // 0: dV, 1: dK
-      const int half = hf;                               // 64-column half of the row
+      // dV / dK leave through shared memory (the K and V tiles are dead once DKV_FULL fired) and four TMA tile stores:
+      // thread-per-row global stores touch 32 different lines per warp instruction (~4000 sector writes per CTA).
+      const int which = g;                               // 0: dV -> the V tile's smem, 1: dK -> the K tile's
+      const int half = hf;                               // 64-column half of the row = one [128 rows][128 B] TMA box
       const float mul = which ? p.scale : 1.f;
-      __nv_bfloat16* dst0 = reinterpret_cast<__nv_bfloat16*>(which ? p.dk : p.dv) + (((int64_t)b * p.Hkv + kvh) * S + s) * HD + 64 * half;
+      uint8_t* srow = (which ? sK : sV) + half * KV_HALF + r * 128;
+      mbar_wait(&bars[KV_FULL], 0, 331);                 // n == 0: the K/V loads issued in the prologue must have landed
 #pragma unroll
       for (int i4 = 0; i4 < 2; ++i4) {
         float o[32];
@@ -481,15 +485,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 32; ++c) o[c] = 0.f;
         }
-        if (key_in) {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            float f[8];
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = o[8 * c8 + e] * mul;
-            store8(dst0 + 32 * i4 + 8 * c8, f);
-          }
+          for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(o[8 * c8 + 2 * e] * mul, o[8 * c8 + 2 * e + 1] * mul);
+          *reinterpret_cast<uint4*>(srow + (((4 * i4 + c8) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+      }
+      fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(5, 512);                            // both softmax groups
+      if (threadIdx.x == 64) {
+        tma_store_4d(&tm_dv, sV, 0, s0, kvh, b);         // rows beyond S are clipped by the TMA unit
+        tma_store_4d(&tm_dv, sV + KV_HALF, 64, s0, kvh, b);
+        tma_store_4d(&tm_dk, sK, 0, s0, kvh, b);
+        tma_store_4d(&tm_dk, sK + KV_HALF, 64, s0, kvh, b);
+        bulk_commit();
+        bulk_wait_read0();
       }
     }
     tc_fence_before();
@@ -559,8 +571,11 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   pp.trace = debug_trace_capacity() >= 24 * 64 ? debug_trace_buffer() : nullptr;
   if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pp.debug_flags = atoi(e);   // bit 0: skip the dQ reduce (timing experiments only)
   if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdk, tdv;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, BQ))) return rc;
+  // dk, dv: contiguous [B, Hkv, S, d] (include/mimic_b200.h)
+  if ((rc = make_map(&tdk, p.dk, p.B, p.Hkv, p.S, (int64_t)p.Hkv * p.S * HD, (int64_t)p.S * HD, HD, BN))) return rc;
+  if ((rc = make_map(&tdv, p.dv, p.B, p.Hkv, p.S, (int64_t)p.Hkv * p.S * HD, (int64_t)p.S * HD, HD, BN))) return rc;
   if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
   if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, BN))) return rc;
   if ((rc = make_map(&tdo, p.d_out, p.B, p.H, p.T, p.go_sb, p.go_sh, p.go_st, BQ))) return rc;
@@ -571,8 +586,8 @@ int bwd(const AttnParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
-  if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
-  else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, pp);
+  if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, pp);
+  else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, pp);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
   return simt::convert_dq_bf16(pp, st);
 }
