@@ -80,6 +80,11 @@ CASES = [
     (2, 2, 2, 64, 192, 128, True, True, True),         # T < S (cache-like), padding
     (1, 2, 2, 200, 200, 128, False, False, True),      # non-causal
     (1, 2, 2, 300, 300, 128, True, True, False),       # inactive (context pass)
+    (1, 2, 2, 130, 66, 128, True, False, True),        # T > S: the first T - S query rows see no key at all
+    (1, 2, 2, 130, 66, 128, True, False, False),       # same, inactive: key tiles without any visible query row
+    (2, 4, 1, 5, 4100, 128, True, True, True),         # short query block against a long cache, GQA 4:1, 65 key tiles
+    (3, 2, 2, 1, 129, 128, False, True, True),         # decode, batch 3, one key past a tile boundary
+    (1, 1, 1, 640, 640, 128, True, False, False),      # several query tiles per CTA slot, one head
 ]
 
 
