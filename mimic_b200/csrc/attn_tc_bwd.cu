@@ -40,7 +40,7 @@ constexpr int KV_TILE = 2 * KV_HALF;       // 32 KB
 constexpr int Q_HALF = BQ * 128;           // [64 rows][128 B] = 8 KB
 constexpr int Q_TILE = 2 * Q_HALF;         // 16 KB
 constexpr int DS_TILE = 128 * 128;         // dS^T [128 keys][64 queries] bf16 = 16 KB
-constexpr int STAGE_BYTES = 32 * HD * 4;   // fp32 dQ staging for 32 query rows, 16 KB (two bulk reduces per tile)
+constexpr int STAGE_BYTES = 32 * HD * 4;   // fp32 dQ staging: two 8 KB buffers of 16 query rows (four bulk reduces per tile)
 constexpr int NQS = 3;                     // Q / dO TMA stages
 constexpr int THREADS = 736;                // warp 0 TMA, warps 1 / 22 MMA issuers A / B, warps 2-9 / 10-17 softmax groups 0 / 1, warps 18-21 drain
 constexpr float LOG2E = 1.4426950408889634f;
@@ -533,20 +533,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (dbg(256)) continue;
       const int rows = min(BQ, T - qt * BQ);
       float* gdst = p.dq_acc + (((int64_t)b * p.H + h) * T + (int64_t)qt * BQ) * HD;
+      // Four 16-row chunks through two 8 KB staging buffers: while the TMA unit reads one buffer for its reduce-add the
+      // threads fill the other (with one 16 KB buffer every half waited for the previous reduce to finish reading:
+      // ~2000 cycles per iteration on the drain warps, as long as the iteration itself).  One commit group per chunk,
+      // so "at most one group still reading" means the buffer about to be refilled is free.
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (did == 0) bulk_wait_read0();                // previous bulk reduce finished reading the staging tile
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float* buf = stage + (q4 & 1) * (16 * HD);
+        if (did == 0) bulk_wait_read1();
         named_bar_sync(4, 128);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) stage[t * HD + c] = half ? v1[t] : v0[t];
+        for (int t = 0; t < 16; ++t) buf[t * HD + c] = (q4 < 2) ? v0[16 * q4 + t] : v1[16 * (q4 - 2) + t];
         fence_proxy_async();
         named_bar_sync(3, 128);
-        if (did == 0 && !dbg(1)) {
-          const int r0 = half * 32, nr = min(32, rows - r0);
-          if (nr > 0) {
-            bulk_reduce_add_f32(gdst + (int64_t)r0 * HD, stage, (uint32_t)nr * HD * 4);
-            bulk_commit();
-          }
+        if (did == 0) {
+          const int r0 = q4 * 16, nr = min(16, rows - r0);
+          if (nr > 0 && !dbg(1)) bulk_reduce_add_f32(gdst + (int64_t)r0 * HD, buf, (uint32_t)nr * HD * 4);
+          bulk_commit();                                 // an empty group keeps the group <-> buffer pairing regular
         }
       }
       if (dtr) stamp(4, i, 3);
