@@ -49,6 +49,27 @@ static inline int make_map(CUtensorMap* m, const void* base, int B, int Hn, int 
   return MIMIC_OK;
 }
 
+// fp32 [N, R, 128] contiguous accumulator (dq_acc) -> 3-D map, box = 32 cols x box_rows rows, no swizzle: the target of the
+// per-warp TMA reduce-adds of the backward (rows past R are clipped, so a ragged last tile cannot touch the next head)
+static inline int make_map_f32_rows(CUtensorMap* m, const void* base, int64_t N, int R, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MIMIC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)128, (cuuint64_t)R, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)128 * 4, (cuuint64_t)R * 128 * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 accumulator) failed with CUresult %d (N=%lld R=%d)", (int)r, (long long)N, R);
+    return MIMIC_ERR_CUDA;
+  }
+  return MIMIC_OK;
+}
 
 }  // namespace tc
 }  // namespace mimic
