@@ -226,10 +226,13 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnParams p) {
 //   Delta' = Delta + dz*exp(lse_c - lse_full)   (folds the visible part of -dz*P^f into P^c(dP-Delta'))
 //   dq_acc = dz * w[h]      dshift[h] += sum_t mu_t g_t    dw[h] += sum_t dz_t q_t    db[h] += sum_t dz_t
 // Reductions: warp shuffle per row, then per-CTA column sums, then ONE atomicAdd per (CTA, h, c).
-template <typename E, int D>
+// ROWS query rows per CTA: 64 for long sequences (few atomics per parameter), 16 when the whole problem is a few
+// thousand rows (a MimIC query pass: T = 128) and the launch is pure latency — 4x the CTAs, a quarter of the serial
+// row batches per CTA.
+template <typename E, int D, int ROWS>
 __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
-  __shared__ float mu_s[64], dz_s[64];
-  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  __shared__ float mu_s[ROWS], dz_s[ROWS];
+  const int t0 = blockIdx.x * ROWS, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = p.T;
   constexpr int EPL = D / 32;  // elements per lane
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
 
   // rows r = warp + 4 i: four rows per batch, all their loads issued before the first reduction (a launch at T = 128 is
   // pure latency: 16 serial row trips per warp cost more than the tensor-core kernel that follows)
-  for (int r4 = 0; r4 < 16; r4 += 4) {
+  for (int r4 = 0; r4 < ROWS / 4; r4 += 4) {
     float gv[4][EPL], ov[4][EPL];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
     const int c = tid;
     float acc_s = 0.f, acc_w = 0.f;
     const float wv = p.active ? p.w[h * D + c] : 0.f;
-    for (int r0 = 0; r0 < 64; r0 += 8) {                 // eight rows of g and q in flight per thread
+    for (int r0 = 0; r0 < ROWS; r0 += 8) {               // eight rows of g and q in flight per thread
       float g8[8], q8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
   }
   if (p.active && tid == 127) {
     float sdz = 0.f;
-    for (int r = 0; r < 64; ++r) sdz += dz_s[r];
+    for (int r = 0; r < ROWS; ++r) sdz += dz_s[r];
     atomicAdd(p.dbias + h, sdz);
   }
 }
@@ -511,8 +514,13 @@ int launch_fwd(const AttnParams& p, cudaStream_t st) {
 template <typename E, int D>
 int launch_bwd(const AttnParams& p, cudaStream_t st) {
   {
-    dim3 grid((p.T + 63) / 64, p.H, p.B);
-    attn_bwd_prep_kernel<E, D><<<grid, 128, 0, st>>>(p);
+    if ((int64_t)p.B * p.H * p.T <= 65536) {
+      dim3 grid((p.T + 15) / 16, p.H, p.B);
+      attn_bwd_prep_kernel<E, D, 16><<<grid, 128, 0, st>>>(p);
+    } else {
+      dim3 grid((p.T + 63) / 64, p.H, p.B);
+      attn_bwd_prep_kernel<E, D, 64><<<grid, 128, 0, st>>>(p);
+    }
     MIMIC_LAUNCH_OK("attn_bwd_prep_kernel(simt)");
   }
   constexpr size_t smem = (size_t)(2 * BM + 2 * BN) * (D + 4) * 4 + (size_t)2 * BM * PLD * 4 + 4 * BM * 4;
@@ -542,8 +550,13 @@ int launch_bwd(const AttnParams& p, cudaStream_t st) {
 
 // pieces of the backward that the tcgen05 path shares (bf16, d = 128)
 int bwd_prep_bf16_d128(const AttnParams& p, cudaStream_t st) {
-  dim3 grid((p.T + 63) / 64, p.H, p.B);
-  attn_bwd_prep_kernel<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p);
+  if ((int64_t)p.B * p.H * p.T <= 65536) {
+    dim3 grid((p.T + 15) / 16, p.H, p.B);
+    attn_bwd_prep_kernel<__nv_bfloat16, 128, 16><<<grid, 128, 0, st>>>(p);
+  } else {
+    dim3 grid((p.T + 63) / 64, p.H, p.B);
+    attn_bwd_prep_kernel<__nv_bfloat16, 128, 64><<<grid, 128, 0, st>>>(p);
+  }
   MIMIC_LAUNCH_OK("attn_bwd_prep_kernel");
   return MIMIC_OK;
 }
