@@ -1,0 +1,95 @@
+"""Randomised shape sweep of the tcgen05 attention kernels against the SIMT fp32-math kernels (independent code:
+different tiling, no TMA / TMEM / mbarrier pipeline): forward output and statistics, backward dq / dk / dv and the
+parameter gradients.  Every pipeline parity (odd / even iteration counts, 1-3 tiles, ragged tails, T != S, GQA groups,
+padding holes, inactive / active, persistent and one-tile-per-CTA forward) gets hit.   python scripts/fuzz_attention.py [N] [seed]"""
+import os
+import random
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mimic_b200 import ops
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def one(rng, idx):
+    d = 128
+    G = rng.choice([1, 1, 2, 4])
+    Hkv = rng.choice([1, 2, 3])
+    H = Hkv * G
+    B = rng.choice([1, 1, 2, 3])
+    kind = rng.choice(["square", "square", "square", "cache", "long_q"])
+    if kind == "square":
+        T = S = rng.choice([1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 200, 255, 256, 257, 320, 383, 384, 500, 640, 777, 1024])
+    elif kind == "cache":
+        T = rng.choice([1, 2, 5, 17, 64, 100])
+        S = T + rng.choice([0, 1, 63, 64, 130, 257, 700])
+    else:
+        S = rng.choice([1, 40, 64, 130])
+        T = S + rng.choice([1, 33, 64, 129])
+    causal = rng.random() < 0.8
+    active = rng.random() < 0.6
+    pad = rng.random() < 0.5
+    g = torch.Generator(device="cuda").manual_seed(1000 + idx)
+    q = torch.randn(B, H, T, d, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Hkv, S, d, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Hkv, S, d, device="cuda", generator=g).bfloat16()
+    do = torch.randn(B, T, H, d, device="cuda", generator=g).bfloat16()
+    km = None
+    if pad:
+        km = torch.rand(B, S, device="cuda", generator=g) > 0.15
+        km[0, : min(S, rng.choice([0, 3, 70]))] = False
+        if not bool(km.any()):
+            km[:, -1] = True
+    sh, w, b = ((torch.randn(H, d, device="cuda", generator=g) * 0.5, torch.randn(H, d, device="cuda", generator=g) * 0.2,
+                 torch.randn(H, device="cuda", generator=g)) if active else (None, None, None))
+    tag = f"#{idx} B{B} H{H}/{Hkv} T{T} S{S} causal{int(causal)} active{int(active)} pad{int(pad)}"
+    res = {}
+    for impl in ("simt", "tcgen05"):
+        out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, km, sh, w, b, causal=causal, active=active,
+                                                                     scale=d ** -0.5, impl=impl)
+        # rows without any visible key are defined as SA = 0 and must not send gradient anywhere
+        vis = torch.isfinite(lse_c).permute(0, 2, 1)[..., None]           # [B,T,H,1]
+        grads = ops.shifted_attention_backward(saved, out, do * vis.to(do.dtype), lse_c, lse_f, mu, causal=causal, active=active,
+                                               scale=d ** -0.5, impl=impl)
+        res[impl] = (out.float(), lse_c, lse_f, mu, grads)
+    a, t = res["simt"], res["tcgen05"]
+    errs = {"out": rel(t[0], a[0])}
+    fin = torch.isfinite(a[1])
+    assert torch.equal(fin, torch.isfinite(t[1])), tag + " visibility of rows differs"
+    errs["lse_c"] = rel(t[1][fin], a[1][fin]) if bool(fin.any()) else 0.0
+    if active:
+        errs["lse_full"] = rel(t[2], a[2])
+        errs["mu"] = rel(t[3], a[3])
+    # dq / dk vanish identically when a row sees a single key (dS = P (dP - Delta) = 0): measure them against the scale of
+    # dv as well, or a 1e-8 reference turns rounding noise into a "relative error" of order one
+    floor = 0.02 * float(a[4][2].double().norm())
+    for i, nme in enumerate(("dq", "dk", "dv") + (("dshift", "dw", "db") if active else ())):
+        ref = a[4][i].double()
+        errs[nme] = float((t[4][i].double() - ref).norm() / (ref.norm() + (floor if i < 2 else 1e-30)))
+    tol = {"out": 8e-3, "lse_c": 1e-4, "lse_full": 1e-4, "mu": 2e-3, "dq": 1.5e-2, "dk": 1.5e-2, "dv": 1.5e-2,
+           "dshift": 1e-3, "dw": 1e-3, "db": 1e-3}
+    bad = {k_: v_ for k_, v_ in errs.items() if not v_ < tol[k_]}
+    return tag, errs, bad
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = random.Random(seed)
+    worst, fails = {}, 0
+    for i in range(n):
+        tag, errs, bad = one(rng, i)
+        for k_, v_ in errs.items():
+            worst[k_] = max(worst.get(k_, 0.0), v_)
+        if bad:
+            fails += 1
+            print("FAIL", tag, {k_: f"{v_:.2e}" for k_, v_ in bad.items()}, flush=True)
+    torch.cuda.synchronize()
+    print(f"{n} cases, {fails} failures; worst rel-L2: " + " ".join(f"{k_}={v_:.1e}" for k_, v_ in worst.items()))
+    sys.exit(1 if fails else 0)
