@@ -105,6 +105,32 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// L2 eviction policies for the two-pass kernels: the row read in pass 1 should still be in L2 for pass 2 (evict_last),
+// everything touched once streams (evict_first).  Without them the CE kernel re-read 80 % of its rows from HBM: 296 CTAs
+// x (304 KB row + 304 KB of gradient being written) outgrow the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_stream_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void stg_hint(void* p, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
+
 int num_sms();
 
 }  // namespace mimic

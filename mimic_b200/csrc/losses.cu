@@ -53,6 +53,14 @@ template <>
 struct Raw8<__nv_bfloat16> {
   uint4 u;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p, uint64_t policy) { u = ldg_hint(p, policy); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8], uint64_t policy) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    stg_hint(p, v, policy);
+  }
   __device__ __forceinline__ void unpack(float (&f)[8]) const {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -69,6 +77,15 @@ struct Raw8<float> {
   __device__ __forceinline__ void load(const float* p) {
     a = *reinterpret_cast<const float4*>(p);
     b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void load(const float* p, uint64_t policy) {
+    const uint4 x = ldg_hint(p, policy), y = ldg_hint(p + 4, policy);
+    a = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
+    b = make_float4(__uint_as_float(y.x), __uint_as_float(y.y), __uint_as_float(y.z), __uint_as_float(y.w));
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8], uint64_t policy) {
+    stg_hint(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])), policy);
+    stg_hint(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])), policy);
   }
   __device__ __forceinline__ void unpack(float (&f)[8]) const {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
@@ -300,6 +317,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
   __shared__ float red[32];
   __shared__ float bc[2];
   __shared__ bool is_last;
+  const uint64_t keep = l2_keep_policy(), stream = l2_stream_policy();
   // every CTA counts the kept rows itself (R labels: a few KB from L2) — no separate counting launch
   float cnt = 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += labels[i] >= 0 ? 1.f : 0.f;
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int c = c0 + u * blockDim.x;
-        if (c < body) raw[u].load(x + head + c * 8);
+        if (c < body) raw[u].load(x + head + c * 8, keep);      // pass 2 wants these lines back from L2
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c = c0 + u * blockDim.x;
-          if (c < body) raw[u].load(x + head + c * 8);
+          if (c < body) raw[u].load(x + head + c * 8, stream);  // last use of the row
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -408,7 +426,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
               for (int e = 0; e < 8; ++e)
                 if (base + e == (int)label) f[e] -= gs;
             }
-            Chunk<T>::store(dx + base, f);
+            Raw8<T>::store(dx + base, f, stream);                 // the gradient streams out: it must not push rows out of L2
           }
         }
       }
@@ -588,13 +606,21 @@ __device__ __forceinline__ void kl_add(KlAcc& k, float z, float y) {
 // 16 bytes starting at an address that is only element-aligned: two aligned 16-byte loads (neighbouring lanes' windows
 // overlap, so the second one hits L1) and a byte-granular funnel shift.  The second vector is only touched when the
 // window really straddles it, so no byte outside the 16-byte granules holding valid data is read.
-__device__ __forceinline__ uint4 load16_window(const void* p) {
+__device__ __forceinline__ uint4 ldg_window_part(const uint4* p, uint64_t policy) {
+  // default L1 caching on purpose: neighbouring lanes' windows overlap, the second aligned vector is an L1 hit
+  uint4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ uint4 load16_window(const void* p, uint64_t policy) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint4* base = reinterpret_cast<const uint4*>(a & ~uintptr_t(15));
   const unsigned o = (unsigned)(a & 15);
-  const uint4 lo = __ldg(base);
+  const uint4 lo = ldg_window_part(base, policy);
   if (o == 0) return lo;
-  const uint4 hi = __ldg(base + 1);
+  const uint4 hi = ldg_window_part(base + 1, policy);
   const unsigned long long q0 = ((unsigned long long)lo.y << 32) | lo.x, q1 = ((unsigned long long)lo.w << 32) | lo.z;
   const unsigned long long q2 = ((unsigned long long)hi.y << 32) | hi.x, q3 = ((unsigned long long)hi.w << 32) | hi.z;
   const unsigned long long x0 = o < 8 ? q0 : q1, x1 = o < 8 ? q1 : q2, x2 = o < 8 ? q2 : q3;
@@ -603,8 +629,8 @@ __device__ __forceinline__ uint4 load16_window(const void* p) {
   const unsigned long long r1 = sh ? (x1 >> sh) | (x2 << (64 - sh)) : x1;
   return make_uint4((unsigned)r0, (unsigned)(r0 >> 32), (unsigned)r1, (unsigned)(r1 >> 32));
 }
-__device__ __forceinline__ void load8_window(const __nv_bfloat16* p, float (&f)[8]) {
-  const uint4 u = load16_window(p);
+__device__ __forceinline__ void load8_window(const __nv_bfloat16* p, float (&f)[8], uint64_t policy) {
+  const uint4 u = load16_window(p, policy);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -613,8 +639,8 @@ __device__ __forceinline__ void load8_window(const __nv_bfloat16* p, float (&f)[
     f[2 * i + 1] = t.y;
   }
 }
-__device__ __forceinline__ void load8_window(const float* p, float (&f)[8]) {
-  const uint4 a = load16_window(p), b = load16_window(p + 4);
+__device__ __forceinline__ void load8_window(const float* p, float (&f)[8], uint64_t policy) {
+  const uint4 a = load16_window(p, policy), b = load16_window(p + 4, policy);
   f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
   f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
 }
@@ -628,6 +654,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
   __shared__ float red[32];
   __shared__ float bc[5];
   __shared__ bool is_last;
+  const uint64_t keep = l2_keep_policy(), stream = l2_stream_policy();
   float cnt = 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += y_row[i] >= 0 ? 1.f : 0.f;
   cnt = block_sum(cnt, red);
@@ -663,8 +690,10 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
       for (int u = 0; u < U; ++u) {
         const int c = c0 + u * blockDim.x;
         if (c < body) {
-          load8(z + head + c * 8, fz[u]);
-          load8_window(y + head + c * 8, fy[u]);
+          Raw8<T> rz;
+          rz.load(z + head + c * 8, keep);                    // both rows come back in pass 2: keep them in L2
+          rz.unpack(fz[u]);
+          load8_window(y + head + c * 8, fy[u], keep);
         }
       }
 #pragma unroll
@@ -738,8 +767,10 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
         for (int u = 0; u < U; ++u) {
           const int c = c0 + u * blockDim.x;
           if (c < body) {
-            load8(z + head + c * 8, fz[u]);
-            load8_window(y + head + c * 8, fy[u]);
+            Raw8<T> rz;
+            rz.load(z + head + c * 8, stream);
+            rz.unpack(fz[u]);
+            load8_window(y + head + c * 8, fy[u], stream);
           }
         }
 #pragma unroll
@@ -748,7 +779,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
           if (c < body) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) fz[u][e] = gs * (__expf(fz[u][e] - lse_z) - __expf(fy[u][e] - lse_y));
-            Chunk<T>::store(d + head + c * 8, fz[u]);
+            Raw8<T>::store(d + head + c * 8, fz[u], stream);
           }
         }
       }
