@@ -131,6 +131,13 @@ __device__ __forceinline__ void stg_hint(void* p, const uint4& v, uint64_t polic
                : "memory");
 }
 
+// 2^x, one MUFU instruction (exp2f() without -use_fast_math wraps it in a range fix-up: FSETP + 2 predicated FMULs)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 int num_sms();
 
 }  // namespace mimic

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
           }
           const float nm = -m * L2E;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s += exp2f(fmaf(f[e], L2E, nm));
+          for (int e = 0; e < 8; ++e) s += fast_ex2(fmaf(f[e], L2E, nm));
         }
       }
     }
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
             float f[8];
             raw[u].unpack(f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = gs * exp2f(fmaf(f[e], L2E, nlse2));
+            for (int e = 0; e < 8; ++e) f[e] = gs * fast_ex2(fmaf(f[e], L2E, nlse2));
             if (c == lab_c && (int)label >= head) {
 #pragma unroll
               for (int e = 0; e < 8; ++e)
@@ -717,10 +717,12 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
             k.ay *= f;
             k.my = cy;
           }
+          constexpr float L2E = 1.4426950408889634f;
+          const float nmz = -k.mz * L2E, nmy = -k.my * L2E;     // exp(x - m) = 2^(x log2e - m log2e): one FFMA + one MUFU
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            k.sz += __expf(fz[u][e] - k.mz);
-            const float ey = __expf(fy[u][e] - k.my);
+            k.sz += fast_ex2(fmaf(fz[u][e], L2E, nmz));
+            const float ey = fast_ex2(fmaf(fy[u][e], L2E, nmy));
             k.sy += ey;
             k.ay = fmaf(ey, fy[u][e] - fz[u][e], k.ay);
           }
@@ -758,6 +760,7 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
     if (threadIdx.x == 0) row_loss[r] = Ay / Sy - lse_y + lse_z;
     if (d) {
       const float gs = grad_scale * inv_n;
+      const float nlz2 = -lse_z * 1.4426950408889634f, nly2 = -lse_y * 1.4426950408889634f;
       // pass 2 (rows come back from L2).  z may alias dz: every element is read before the same thread writes it.
       for (int i = threadIdx.x; i < head; i += blockDim.x)
         d[i] = from_f32<T>(gs * (__expf(to_f32(z[i]) - lse_z) - __expf(to_f32(y[i]) - lse_y)));
@@ -778,7 +781,8 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
           const int c = c0 + u * blockDim.x;
           if (c < body) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) fz[u][e] = gs * (__expf(fz[u][e] - lse_z) - __expf(fy[u][e] - lse_y));
+            for (int e = 0; e < 8; ++e)
+              fz[u][e] = gs * (fast_ex2(fmaf(fz[u][e], 1.4426950408889634f, nlz2)) - fast_ex2(fmaf(fy[u][e], 1.4426950408889634f, nly2)));
             Raw8<T>::store(d + head + c * 8, fz[u], stream);
           }
         }
