@@ -37,7 +37,8 @@ def test_random_shapes_persistent_forward(monkeypatch):
         assert not bad, (tag, bad)
 
 
-@pytest.mark.parametrize("B,H,Hkv,T,pad", [(2, 16, 4, 1536, True), (3, 12, 12, 1100, False), (5, 8, 2, 2048, True)])
+@pytest.mark.parametrize("B,H,Hkv,T,pad", [(2, 16, 4, 1536, True), (3, 12, 12, 1100, False), (5, 8, 2, 2048, True),
+                                          (100, 2, 1, 1100, True)])   # last: key-bit tables too big for all rows -> rebuilt per item
 def test_persistent_forward_several_items_per_cta(monkeypatch, B, H, Hkv, T, pad):
     """More work items than the 2 x #SMs persistent CTAs: every CTA walks several (query tile, head, batch) items, so the
     Q hand-over (Q_EMPTY), the running K/V ring phases, the per-batch-row key bits and the O reuse across items are all on
