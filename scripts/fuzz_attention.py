@@ -23,9 +23,13 @@ def one(rng, idx):
     Hkv = rng.choice([1, 2, 3])
     H = Hkv * G
     B = rng.choice([1, 1, 2, 3])
-    kind = rng.choice(["square", "square", "square", "cache", "long_q"])
+    kind = rng.choice(["square", "square", "square", "cache", "long_q"] + (["big"] if os.environ.get("FUZZ_BIG") else []))
     if kind == "square":
         T = S = rng.choice([1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 200, 255, 256, 257, 320, 383, 384, 500, 640, 777, 1024])
+    elif kind == "big":                                   # several waves of CTAs, long key loops
+        T = S = rng.choice([1500, 2048, 2500, 3200])
+        B, Hkv, G = rng.choice([1, 2]), rng.choice([2, 4, 8]), rng.choice([1, 4])
+        H = Hkv * G
     elif kind == "cache":
         T = rng.choice([1, 2, 5, 17, 64, 100])
         S = T + rng.choice([0, 1, 63, 64, 130, 257, 700])
