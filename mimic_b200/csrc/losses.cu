@@ -2,6 +2,7 @@
 // (M), fused LM-loss cross-entropy forward+backward (C), and the on-device clip + AdamW step.
 // All are single launches over all layers / rows, 16-byte vectorised, streaming (L1 no-allocate)
 // loads and stores, persistent grid-stride over rows with grids sized from the SM count.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -574,6 +575,153 @@ __global__ void __launch_bounds__(256) cos_fwd_bwd_kernel(const void* const* __r
   }
 }
 
+// Variant with an asynchronous two-stage pipeline through shared memory (cp.async, 16 bytes per copy): the rows of H
+// and H' of item i+1 stream into stage (i+1)&1 while item i is reduced and its gradient written out of stage i&1, so
+// the block-wide barriers of the reduction no longer leave the memory system idle (the register version loads, waits,
+// synchronises three times, stores — 4.25 TB/s; a register prefetch of the next item costs too many registers).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int NS>
+__global__ void __launch_bounds__(256) cos_fwd_bwd_pipe_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
+                                                               const T* __restrict__ hp,
+                                                               const int32_t* __restrict__ row_to_compact,
+                                                               const float* __restrict__ row_w,
+                                                               void* const* __restrict__ dh_ptrs, float grad_scale, int L,
+                                                               int rows, int N, int D, float* __restrict__ partial,
+                                                               unsigned int* __restrict__ counter, float* __restrict__ loss) {
+  extern __shared__ __align__(16) uint8_t cos_smem[];    // [NS stages][H row | H' row], D * sizeof(T) bytes each
+  __shared__ float red[3][32];
+  __shared__ float bc[3];
+  __shared__ bool is_last;
+  const int chunks = D / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t items = (int64_t)L * rows;
+  const size_t row_bytes = (size_t)D * sizeof(T);
+  constexpr int VPC = sizeof(T) == 2 ? 1 : 2;            // 16-byte vectors per 8-element chunk
+  auto stage_h = [&](int st) { return reinterpret_cast<T*>(cos_smem + (size_t)st * 2 * row_bytes); };
+  auto stage_t = [&](int st) { return reinterpret_cast<T*>(cos_smem + (size_t)st * 2 * row_bytes + row_bytes); };
+  auto issue = [&](int64_t it, int st) -> int {          // returns the compact row (or -1: nothing to load)
+    int c = -1;
+    if (it < items) {
+      const int l = (int)(it / rows), r = (int)(it % rows);
+      c = row_to_compact[r];
+      if (c >= 0) {
+        const T* h = reinterpret_cast<const T*>(h_ptrs[l]) + (int64_t)r * h_row_stride;
+        const T* t = hp + ((int64_t)l * N + c) * D;
+        T* sh = stage_h(st);
+        T* stt = stage_t(st);
+        for (int v = threadIdx.x; v < chunks * VPC; v += blockDim.x) {
+          cp_async16(reinterpret_cast<uint4*>(sh) + v, reinterpret_cast<const uint4*>(h) + v);
+          cp_async16(reinterpret_cast<uint4*>(stt) + v, reinterpret_cast<const uint4*>(t) + v);
+        }
+      }
+    }
+    cp_async_commit();                                   // always one group per item: the wait counts stay regular
+    return c;
+  };
+  float acc = 0.f;
+  int cq[NS];                                            // compact rows of the items in flight (item k lives in stage k % NS)
+#pragma unroll
+  for (int j = 0; j < NS - 1; ++j) cq[j] = issue(blockIdx.x + (int64_t)j * gridDim.x, j);
+  int k = 0;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++k) {
+    const int st = k % NS;
+    // item k + NS - 1 goes into the stage that the barrier ending item k - 1 released
+    cq[NS - 1] = issue(it + (int64_t)(NS - 1) * gridDim.x, (k + NS - 1) % NS);
+    cp_async_wait<NS - 1>();                             // all but the newest NS - 1 groups have landed: item k is in stage st
+    __syncthreads();
+    const int l = (int)(it / rows), r = (int)(it % rows);
+    const int c = cq[0];
+#pragma unroll
+    for (int j = 0; j < NS - 1; ++j) cq[j] = cq[j + 1];
+    T* dh = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) + (int64_t)r * D : nullptr;
+    if (c < 0) {
+      if (dh) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) Chunk<T>::store(dh + ch * 8, z);
+      }
+      __syncthreads();
+      continue;
+    }
+    const T* sh = stage_h(st);
+    const T* stt = stage_t(st);
+    float dot = 0.f, na = 0.f, nb = 0.f;
+    for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+      float a[8], b[8];
+      load8(sh + ch * 8, a);
+      load8(stt + ch * 8, b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dot = fmaf(a[e], b[e], dot);
+        na = fmaf(a[e], a[e], na);
+        nb = fmaf(b[e], b[e], nb);
+      }
+    }
+    dot = warp_sum(dot);
+    na = warp_sum(na);
+    nb = warp_sum(nb);
+    if (lane == 0) {
+      red[0][warp] = dot;
+      red[1][warp] = na;
+      red[2][warp] = nb;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float v0 = lane < nw ? red[0][lane] : 0.f, v1 = lane < nw ? red[1][lane] : 0.f, v2 = lane < nw ? red[2][lane] : 0.f;
+      v0 = warp_sum(v0);
+      v1 = warp_sum(v1);
+      v2 = warp_sum(v2);
+      if (lane == 0) {
+        bc[0] = v0;
+        bc[1] = v1;
+        bc[2] = v2;
+      }
+    }
+    __syncthreads();
+    const float ha = fmaxf(sqrtf(bc[1]), 1e-8f), hb = fmaxf(sqrtf(bc[2]), 1e-8f);
+    const float inv = 1.f / (ha * hb);
+    const float cs = bc[0] * inv;
+    const float w = row_w[c];
+    if (threadIdx.x == 0) acc += w * (1.f - cs);
+    if (dh) {
+      const float gw = -grad_scale * w;
+      const float k1 = gw * inv, k2 = gw * cs / (ha * ha);
+      for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+        float a[8], b[8], g[8];
+        load8(sh + ch * 8, a);
+        load8(stt + ch * 8, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = k1 * b[e] - k2 * a[e];
+        Chunk<T>::store(dh + ch * 8, g);
+      }
+    }
+    __syncthreads();                                     // stage st and bc[] are free again
+  }
+  cp_async_wait<0>();
+  acc = block_sum(acc, red[0]);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
+    tot = block_sum(tot, red[0]);
+    if (threadIdx.x == 0) {
+      loss[0] = tot;
+      *counter = 0u;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Logits KL divergence (Strategy.LOGITS_KL_DIV, src/shift_model.py:181-191), forward + backward in one launch:
 //   loss = (1/R) sum_r KL( softmax(y_r) || softmax(z_r) ),   dz = grad_scale / R * (softmax(z) - softmax(y))
@@ -1011,6 +1159,34 @@ extern "C" int mimic_cos_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride
   float* partial = static_cast<float*>(workspace) + 4;
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
   // (a warp-per-row variant that re-reads the row from L2 for the gradient pass was measured: 1.9 TB/s against 4.25 TB/s)
+  static const int variant = getenv("MIMIC_COS_VARIANT") ? atoi(getenv("MIMIC_COS_VARIANT")) : 1;   // 1: cp.async pipeline, 0: registers
+  constexpr int COS_NS = 2;       // measured: 3 stages (48 KB, 4 CTAs/SM) 4.24 TB/s, 2 stages 4.56 TB/s
+  const size_t pipe_smem = (size_t)2 * COS_NS * D * (h_dtype == MIMIC_BF16 ? 2 : 4);
+  if (variant == 1 && pipe_smem <= 96 * 1024 && (h_dtype == MIMIC_BF16 || h_dtype == MIMIC_F32)) {
+    // every CTA resident at once (a partial second wave is a tail): CTAs per SM by shared memory, at most 8
+    const int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / (pipe_smem + 1024));
+    const int64_t cap = (int64_t)num_sms() * per_sm, n_items = (int64_t)L * rows;
+    const int pgrid = (int)(n_items < cap ? n_items : cap);
+    if (h_dtype == MIMIC_BF16) {
+      static size_t conf = 0;
+      if (pipe_smem > conf) {
+        MIMIC_CUDA_OK(cudaFuncSetAttribute(cos_fwd_bwd_pipe_kernel<__nv_bfloat16, COS_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+        conf = pipe_smem;
+      }
+      cos_fwd_bwd_pipe_kernel<__nv_bfloat16, COS_NS><<<pgrid, 256, pipe_smem, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+                                                                          row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+    } else {
+      static size_t conf = 0;
+      if (pipe_smem > conf) {
+        MIMIC_CUDA_OK(cudaFuncSetAttribute(cos_fwd_bwd_pipe_kernel<float, COS_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+        conf = pipe_smem;
+      }
+      cos_fwd_bwd_pipe_kernel<float, COS_NS><<<pgrid, 256, pipe_smem, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w,
+                                                                   dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+    }
+    MIMIC_LAUNCH_OK("cos_fwd_bwd_pipe_kernel");
+    return MIMIC_OK;
+  }
   const bool small = D <= 256 * 8 * 2;
   if (h_dtype == MIMIC_BF16 && small)
     cos_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
