@@ -100,6 +100,40 @@ MIMIC_API int mimic_shifted_attn_bwd(const mimic_attn_desc_t* desc,
                            float* dshift, float* dw, float* dbias,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same backward with one more incoming gradient: d_lse_full fp32 [B,H,T] (or NULL) = dL/d lse_full from
+ * OUTSIDE the op.  The non-MULTI_HEAD variant of do_shift (src/shift_encoder.py:689-692, 705-707) averages
+ * log_Z2 over the heads before the sigmoid, so mu is formed by the host from the lse_full this op returns
+ * (forward run with shift = w = bias = 0: out = SA) and its gradient re-enters here: dS += d_lse_full * P^f. */
+MIMIC_API int mimic_shifted_attn_bwd_lse(const mimic_attn_desc_t* desc,
+                           const void* q, const void* k, const void* v,
+                           const uint8_t* key_mask,
+                           const float* shift, const float* w, const float* bias,
+                           const void* out, const void* d_out,
+                           int64_t go_sb, int64_t go_st, int64_t go_sh,
+                           const float* lse_c, const float* lse_full, const float* mu,
+                           const float* d_lse_full,
+                           void* dq, void* dk, void* dv,
+                           float* dshift, float* dw, float* dbias,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Norm-preserving vector shift of a module output: y = u / |u| * |h|, u = h + scale * shift.
+ * Replaces the hook body of AttnFFNShift._shift_hook (src/shift_encoder.py:222-247; the LIVE baseline,
+ * config/encoder/licv.yaml) and of AttnApproximator's optional FFN hook (src/shift_encoder.py:653-672), and
+ * their autograd.
+ *   h [N, D] rows of stride h_row_stride elements; shift fp32 [D] ({attn,ffn}_shift[layer]); scale: device
+ *   pointer to ONE fp32 ({attn,ffn}_shift_scale[layer]) or NULL for 1; y [N, D] contiguous, dtype of h.
+ *   Backward: dh [N, D] contiguous is overwritten; gsum fp32 [D] is ACCUMULATED INTO with the column sums of
+ *   dL/du, from which the caller forms  dshift = scale * gsum  and  dscale = gsum . shift.
+ *   D: multiple of 8, at most 8192.  Norms and all arithmetic in fp32.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_norm_shift_fwd(const void* h, int64_t h_row_stride, int32_t dtype,
+                         const float* shift, const float* scale, void* y,
+                         int32_t N, int32_t D, void* stream);
+MIMIC_API int mimic_norm_shift_bwd(const void* h, int64_t h_row_stride, const void* dy, int64_t dy_row_stride,
+                         int32_t dtype, const float* shift, const float* scale,
+                         void* dh, float* gsum, int32_t N, int32_t D, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Record path: gather the selected token rows of one layer's recorded module output straight
  * into the preallocated [L, N, D] buffer.  Replaces record_hook (src/shift_encoder.py:115-120)

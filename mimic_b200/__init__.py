@@ -5,9 +5,9 @@ it is missing and cannot be built): there is no CPU or eager fallback."""
 from . import _lib  # noqa: F401  (fail loudly, first)
 from . import ops
 from .model_base import HookedModel, try_inject_params
-from .shift_encoder import (AttnApproxHandle, AttnApproximator, BaseHookEncoder, MultiheadLinear, RecordPlan,
+from .shift_encoder import (AttnApproxHandle, AttnApproximator, AttnFFNShift, BaseHookEncoder, MultiheadLinear, RecordPlan,
                             ShiftStrategy)
 from .shift_model import ShiftModel, Strategy
 
-__all__ = ["ops", "HookedModel", "try_inject_params", "AttnApproxHandle", "AttnApproximator", "BaseHookEncoder",
+__all__ = ["ops", "HookedModel", "try_inject_params", "AttnApproxHandle", "AttnApproximator", "AttnFFNShift", "BaseHookEncoder",
            "MultiheadLinear", "RecordPlan", "ShiftStrategy", "ShiftModel", "Strategy"]

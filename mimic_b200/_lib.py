@@ -36,6 +36,12 @@ EXPORTS = {
     "mimic_shifted_attn_bwd_workspace": (C.c_size_t, [C.POINTER(AttnDesc)]),
     "mimic_shifted_attn_bwd": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 9 + [C.c_int64] * 3 +
                                [C.c_void_p] * 10 + [C.c_size_t, C.c_void_p]),
+    "mimic_shifted_attn_bwd_lse": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 9 + [C.c_int64] * 3 +
+                                   [C.c_void_p] * 11 + [C.c_size_t, C.c_void_p]),
+    "mimic_norm_shift_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "mimic_norm_shift_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mimic_record_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "mimic_mse_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),

@@ -69,6 +69,18 @@ extern "C" int mimic_shifted_attn_bwd(const mimic_attn_desc_t* desc, const void*
                                       int64_t go_st, int64_t go_sh, const float* lse_c, const float* lse_full,
                                       const float* mu, void* dq, void* dk, void* dv, float* dshift, float* dw,
                                       float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  return mimic_shifted_attn_bwd_lse(desc, q, k, v, key_mask, shift, w, bias, out, d_out, go_sb, go_st, go_sh, lse_c,
+                                    lse_full, mu, nullptr, dq, dk, dv, dshift, dw, dbias, workspace, workspace_bytes,
+                                    stream);
+}
+
+extern "C" int mimic_shifted_attn_bwd_lse(const mimic_attn_desc_t* desc, const void* q, const void* k, const void* v,
+                                          const uint8_t* key_mask, const float* shift, const float* w,
+                                          const float* bias, const void* out, const void* d_out, int64_t go_sb,
+                                          int64_t go_st, int64_t go_sh, const float* lse_c, const float* lse_full,
+                                          const float* mu, const float* d_lse_full, void* dq, void* dk, void* dv,
+                                          float* dshift, float* dw, float* dbias, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
   AttnParams p{};
   int rc = fill(desc, p);
   if (rc) return rc;
@@ -79,6 +91,7 @@ extern "C" int mimic_shifted_attn_bwd(const mimic_attn_desc_t* desc, const void*
   if (p.active)
     MIMIC_CHECK_ARG(shift && w && bias && lse_full && mu && dshift && dw && dbias,
                     "active shift needs shift/w/bias/lse_full/mu and dshift/dw/dbias");
+  MIMIC_CHECK_ARG(p.active || !d_lse_full, "d_lse_full needs an active handle (lse_full is only produced then)");
   if (go_sb || go_st || go_sh) {
     MIMIC_CHECK_ARG(go_sb % 8 == 0 && go_st % 8 == 0 && go_sh % 8 == 0, "d_out strides must be multiples of 8");
     p.go_sb = go_sb; p.go_st = go_st; p.go_sh = go_sh;
@@ -95,6 +108,7 @@ extern "C" int mimic_shifted_attn_bwd(const mimic_attn_desc_t* desc, const void*
   p.dz_ws = reinterpret_cast<float*>(ws);
   p.q = q; p.k = k; p.v = v; p.key_mask = key_mask; p.shift = shift; p.w = w; p.bias = bias;
   p.out = const_cast<void*>(out); p.d_out = d_out;
+  p.d_lse_full = d_lse_full;
   p.lse_c = const_cast<float*>(lse_c); p.lse_full = const_cast<float*>(lse_full); p.mu = const_cast<float*>(mu);
   p.dq = dq; p.dk = dk; p.dv = dv; p.dshift = dshift; p.dw = dw; p.dbias = dbias;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

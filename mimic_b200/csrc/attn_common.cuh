@@ -20,6 +20,7 @@ struct AttnParams {
   float *lse_c, *lse_full, *mu;
   // backward only
   const void* d_out;
+  const float* d_lse_full = nullptr;   // optional gradient arriving at lse_full from outside the op (head-averaged mu variant)
   void *dq, *dk, *dv;
   float *dshift, *dw, *dbias;
   float *dq_acc, *delta_ws, *dz_ws;

@@ -273,14 +273,18 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
           if (p.active) {
             mu = p.mu[row0 + t];
             dz = mu * (1.f - mu) * dmu;
+            // a gradient g arriving at lse_full itself adds g * P^f to dS, i.e. acts like dz = -g on the score path only
+            // (it has no z1 = q.W + b behind it, so the parameter / dq-seed sums below keep the op's own dz)
+            const float dz_all = dz - (p.d_lse_full ? p.d_lse_full[row0 + t] : 0.f);
             const float lc = p.lse_c[row0 + t];
             const float rho = (lc == -INFINITY) ? 0.f : expf(lc - p.lse_full[row0 + t]);
-            dl = gout - mu * dmu + dz * rho;
+            dl = gout - mu * dmu + dz_all * rho;
+            p.dz_ws[row0 + t] = dz_all;
           } else {
             dl = gout;
+            p.dz_ws[row0 + t] = 0.f;
           }
           p.delta_ws[row0 + t] = dl;
-          p.dz_ws[row0 + t] = dz;
         }
         mu_s[r] = mu;
         dz_s[r] = dz;

@@ -134,8 +134,9 @@ def shifted_attention_forward(q, k, v, key_mask, shift, w, bias, *, causal, acti
 
 
 def shifted_attention_backward(saved, out, d_out, lse_c, lse_full, mu, *, causal, active, scale, impl="auto",
-                               dshift=None, dw=None, dbias=None):
-    """Raw backward.  dshift/dw/dbias (fp32) are ACCUMULATED INTO when given, else allocated zeroed."""
+                               dshift=None, dw=None, dbias=None, d_lse_full=None):
+    """Raw backward.  dshift/dw/dbias (fp32) are ACCUMULATED INTO when given, else allocated zeroed.
+    d_lse_full [B,H,T] fp32: optional gradient arriving at lse_full from outside the op."""
     q, k, v, key_mask, shift, w, bias = saved
     B, H, T, d = q.shape
     if d_out.stride(-1) != 1 or any(s % 8 for s in d_out.stride()[:-1]) or d_out.data_ptr() % 16:
@@ -152,11 +153,14 @@ def shifted_attention_backward(saved, out, d_out, lse_c, lse_full, mu, *, causal
     nbytes = lib.mimic_shifted_attn_bwd_workspace(desc)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     _ev = timer.start(f"attn_bwd_{'active' if active else 'inactive'}_T{T}_S{k.shape[2]}")
-    check(lib.mimic_shifted_attn_bwd(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w), _ptr(bias),
-                                     _ptr(out), _ptr(d_out), d_out.stride(0), d_out.stride(1), d_out.stride(2),
-                                     _ptr(lse_c), _ptr(lse_full), _ptr(mu), _ptr(dq), _ptr(dk), _ptr(dv),
-                                     _ptr(dshift), _ptr(dw), _ptr(dbias), _ptr(ws), nbytes, _stream()),
-          "mimic_shifted_attn_bwd")
+    if d_lse_full is not None:
+        d_lse_full = d_lse_full.float().contiguous()
+    check(lib.mimic_shifted_attn_bwd_lse(desc, _ptr(q), _ptr(k), _ptr(v), _ptr(key_mask), _ptr(shift), _ptr(w),
+                                         _ptr(bias), _ptr(out), _ptr(d_out), d_out.stride(0), d_out.stride(1),
+                                         d_out.stride(2), _ptr(lse_c), _ptr(lse_full), _ptr(mu), _ptr(d_lse_full),
+                                         _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dshift), _ptr(dw), _ptr(dbias), _ptr(ws),
+                                         nbytes, _stream()),
+          "mimic_shifted_attn_bwd_lse")
     timer.stop(_ev)
     _count(3)
     return dq, dk, dv, dshift, dw, dbias
@@ -197,6 +201,104 @@ class _ShiftedAttention(torch.autograd.Function):
         else:
             dshift, dw, dbias = (g.to(dt) for g, dt in zip((dshift, dw, dbias), ctx.param_dtypes))
         return dq, dk, dv, dshift, dw, dbias, None, None, None, None, None, None
+
+
+class _AttentionWithFullLse(torch.autograd.Function):
+    """(SA [B,T,H,d], lse_full [B,H,T]) from ONE pass of the fused kernel, both differentiable: the op is run active
+    with shift = w = bias = 0, so its own mu term vanishes and out == SA; the gradient that arrives at lse_full goes
+    back in through mimic_shifted_attn_bwd_lse."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, causal, scale, impl):
+        B, H, T, d = q.shape
+        zero_hd = torch.zeros(H, d, dtype=torch.float32, device=q.device)
+        zero_h = torch.zeros(H, dtype=torch.float32, device=q.device)
+        out, lse_c, lse_full, mu, saved = shifted_attention_forward(
+            q, k, v, key_mask, zero_hd, zero_hd, zero_h, causal=causal, active=True, scale=scale, impl=impl)
+        ctx.saved = saved
+        ctx.stats = (out, lse_c, lse_full, mu)
+        ctx.cfg = (causal, scale, impl)
+        return out, lse_full
+
+    @staticmethod
+    def backward(ctx, d_out, d_lse_full):
+        causal, scale, impl = ctx.cfg
+        out, lse_c, lse_full, mu = ctx.stats
+        if d_out is None:
+            d_out = torch.zeros_like(out)
+        dq, dk, dv, _, _, _ = shifted_attention_backward(
+            ctx.saved, out, d_out, lse_c, lse_full, mu, causal=causal, active=True, scale=scale, impl=impl,
+            d_lse_full=d_lse_full)
+        return dq, dk, dv, None, None, None, None
+
+
+def attention_with_full_lse(q, k, v, key_mask=None, *, causal=True, scale=None, impl="auto"):
+    """Masked attention output plus the UNMASKED log-sum-exp of the scores (log_Z2 of src/shift_encoder.py:697-703)
+    per head — what the non-MULTI_HEAD variant of do_shift averages over the heads (705-707)."""
+    if scale is None:
+        scale = 1.0 / math.sqrt(q.shape[-1])
+    return _AttentionWithFullLse.apply(q, k, v, key_mask, causal, scale, impl)
+
+
+# ------------------------------------------------------------------------------------------------
+class _NormShift(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, shift, scale):
+        D = h.shape[-1]
+        h2 = h.reshape(-1, D)
+        if h2.stride(-1) != 1 or h2.stride(0) % 8 or h2.data_ptr() % 16:
+            h2 = h2.contiguous()
+        sh = shift.detach().float().contiguous()
+        sc = None if scale is None else scale.detach().float().reshape(1).contiguous()
+        y = torch.empty(h2.shape, dtype=h.dtype, device=h.device)
+        if h2.shape[0]:
+            _ev = timer.start("norm_shift_fwd")
+            check(lib.mimic_norm_shift_fwd(_ptr(h2), h2.stride(0), _DT[h.dtype], _ptr(sh), _ptr(sc), _ptr(y),
+                                           h2.shape[0], D, _stream()), "mimic_norm_shift_fwd")
+            timer.stop(_ev)
+            _count(1)
+        ctx.saved = (h2, sh, sc)
+        ctx.meta = (h.shape, shift.dtype, None if scale is None else (scale.dtype, scale.shape))
+        return y.view(h.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h2, sh, sc = ctx.saved
+        shape, shift_dtype, scale_meta = ctx.meta
+        D = shape[-1]
+        dy2 = dy.reshape(-1, D)
+        if dy2.dtype != h2.dtype:
+            dy2 = dy2.to(h2.dtype)
+        if dy2.stride(-1) != 1 or dy2.stride(0) % 8 or dy2.data_ptr() % 16:
+            dy2 = dy2.contiguous()
+        dh = torch.empty(h2.shape, dtype=h2.dtype, device=h2.device)
+        gsum = torch.zeros(D, dtype=torch.float32, device=h2.device)
+        if h2.shape[0]:
+            _ev = timer.start("norm_shift_bwd")
+            check(lib.mimic_norm_shift_bwd(_ptr(h2), h2.stride(0), _ptr(dy2), dy2.stride(0), _DT[h2.dtype], _ptr(sh),
+                                           _ptr(sc), _ptr(dh), _ptr(gsum), h2.shape[0], D, _stream()),
+                  "mimic_norm_shift_bwd")
+            timer.stop(_ev)
+            _count(1)
+        dshift = (gsum if sc is None else gsum * sc).to(shift_dtype)
+        dscale = None
+        if scale_meta is not None:
+            dscale = torch.dot(gsum, sh).to(scale_meta[0]).reshape(scale_meta[1])
+        return dh.view(shape), dshift, dscale
+
+
+def norm_shift(h: torch.Tensor, shift: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = u / |u| * |h| with u = h + scale * shift: the norm-preserving shift hook of AttnFFNShift
+    (src/shift_encoder.py:233-240) and of AttnApproximator's FFN hook (661-667), one launch each way.
+    h [..., D] bf16/fp32, shift [D], scale a one-element tensor or None (= 1).  Output in h's dtype."""
+    _require_cuda(h, shift, scale)
+    if h.dtype not in _DT:
+        raise MimicError(f"norm_shift: h must be bf16 or fp32 (got {h.dtype})")
+    D = h.shape[-1]
+    if D % 8 or D > 8192 or shift.shape != (D,):
+        raise MimicError(f"norm_shift: hidden size {D} unsupported (multiple of 8, at most 8192) or shift shape "
+                         f"{tuple(shift.shape)} != ({D},)")
+    return _NormShift.apply(h, shift, scale)
 
 
 def shifted_attention(q, k, v, shift=None, w=None, bias=None, key_mask=None, *, causal=True, active=True,

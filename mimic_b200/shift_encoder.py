@@ -22,6 +22,7 @@ from functools import partial
 from typing import Callable, Dict, List, Optional, Union
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -148,6 +149,50 @@ class BaseHookEncoder(nn.Module):
                                     if hasattr(self, "ffn_hidden_states") else None),
             },
         )
+
+
+class AttnFFNShift(BaseHookEncoder):
+    """Learnable norm-preserving vector shift after the attention and / or MLP output of every decoder layer
+    (src/shift_encoder.py:143-247): the LIVE baseline (config/encoder/licv.yaml) and, with both strategies null, the
+    plain recording / LoRA encoder (config/encoder/lora.yaml).  Same constructor, parameter names
+    ({attn,ffn}_shift [L,D], {attn,ffn}_shift_scale [L]) and hook dictionary as the reference; the hook body is one
+    CUDA launch (ops.norm_shift) instead of seven elementwise / reduction ones."""
+
+    def __init__(self, lmm, attn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy(0),
+                 ffn_strategy: Union[str, ShiftStrategy, None] = ShiftStrategy(0), shift_scale_init_value=None):
+        super().__init__(lmm, attn_strategy, ffn_strategy)
+        for prefix in ("attn", "ffn"):
+            strategy = getattr(self, f"{prefix}_strategy")
+            if ShiftStrategy.MULTI_HEAD in strategy:
+                raise ValueError(
+                    f" ShiftStrategy.MULTI_HEAD is not supported, since shift is inserted after {prefix} output")
+            if ShiftStrategy.VECTOR_SHIFT not in strategy:
+                continue
+            setattr(self, f"{prefix}_shift",
+                    nn.Parameter(torch.empty(self.lmm_layers, self.lmm_hidden_dim).normal_(mean=0.0, std=0.01)))
+            if ShiftStrategy.LEARNABLE_SHIFT_SCALE in strategy:
+                init = shift_scale_init_value if shift_scale_init_value else 1.0
+                setattr(self, f"{prefix}_shift_scale", nn.Parameter(torch.full([self.lmm_layers], init)))
+            else:
+                self.register_buffer(f"{prefix}_shift_scale", torch.ones(self.lmm_layers))
+
+    def register_shift_hooks(self, **kwargs):
+        return self.register_hooks(
+            "register_forward_hook",
+            [self.decoder_self_attn_name, self.decoder_mlp_name],
+            {"attn_hook": self._shift_hook("attn") if hasattr(self, "attn_shift") else None,
+             "ffn_hook": self._shift_hook("ffn") if hasattr(self, "ffn_shift") else None})
+
+    def _shift_hook(self, prefix):
+        def hook(m, inputs, outputs, module_name, **kw):
+            layer_idx = int(re.findall(r"\d+", module_name)[0])
+            shift = getattr(self, f"{prefix}_shift", None)
+            hidden_states, *rest = outputs if isinstance(outputs, tuple) else (outputs,)
+            if shift is not None:
+                scale = getattr(self, f"{prefix}_shift_scale")
+                hidden_states = ops.norm_shift(hidden_states, shift[layer_idx], scale[layer_idx])
+            return (hidden_states, *rest) if isinstance(outputs, tuple) else hidden_states
+        return hook
 
 
 class MultiheadLinear(nn.Module):                      # src/shift_encoder.py:547-556
@@ -317,9 +362,7 @@ class AttnApproximator(BaseHookEncoder):
             def hook(m, inputs, outputs, module_name, **kw):
                 layer_idx = int(re.findall(r"\d+", module_name)[0])
                 hidden_states, *rest = outputs if isinstance(outputs, tuple) else (outputs,)
-                shifted = hidden_states + self.ffn_shift[layer_idx][None, None, :]
-                hidden_states = (shifted / shifted.norm(dim=-1, keepdim=True)
-                                 * hidden_states.norm(dim=-1, keepdim=True))
+                hidden_states = ops.norm_shift(hidden_states, self.ffn_shift[layer_idx])
                 return (hidden_states, *rest) if isinstance(outputs, tuple) else hidden_states
             registered_hooks.update(
                 self.register_hooks("register_forward_hook", [self.decoder_mlp_name], {"ffn_hook": hook}))
@@ -330,34 +373,66 @@ class AttnApproximator(BaseHookEncoder):
         need = ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD
         return (self.attn_strategy & need) == need
 
+    def _single_head_mu(self, layer_idx, q, lse_full):
+        """mu [B,T,1] of the non-MULTI_HEAD variant (src/shift_encoder.py:689-692, 705-712): log_Z2 averaged over the
+        heads, log_Z1 = Linear(D, 1) of the flattened query.  lse_full [B,H,T] comes from the fused kernel."""
+        B, H, T, d = q.shape
+        lin = self.log_Z1_lin[layer_idx]
+        log_z2 = lse_full.transpose(1, 2).mean(-1, keepdim=True)
+        q_flat = q.transpose(1, 2).reshape(B, T, H * d)
+        log_z1 = F.linear(q_flat.float(), lin.weight.float(), lin.bias.float())
+        return torch.exp(log_z1 - torch.logaddexp(log_z1, log_z2))
+
     def fused_attention(self, layer_idx, q, k, v, key_mask, causal, scale=None):
         """[B,H,T,d] x [B,Hkv,S,d] -> [B,T,H,d]; plain masked attention when the handle is inactive
-        (src/shift_encoder.py:685, 732)."""
+        (src/shift_encoder.py:685, 732).  The mimic.yaml strategy runs entirely inside the fused kernel; the other
+        AttnApproximator variants take SA (and the unmasked log-sum-exp) from the same kernel and finish with a
+        broadcast add."""
         active = self.attn_shift_handles[layer_idx].active
-        if active and not self._fused_ok():
-            raise NotImplementedError(
-                "the fused CUDA path implements the mimic.yaml strategy "
-                "(VECTOR_SHIFT | LEARNABLE_SHIFT_SCALE | MULTI_HEAD); got " + repr(self.attn_strategy))
         if not active:
             return ops.shifted_attention(q, k, v, None, None, None, key_mask, causal=causal, active=False,
                                          scale=scale, impl=self.attn_impl)
-        lin = self.log_Z1_lin[layer_idx]
-        sink = self.grad_sinks[layer_idx] if self.grad_sinks is not None else None
-        return ops.shifted_attention(q, k, v, self.attn_shift[layer_idx], lin.weight, lin.bias, key_mask,
-                                     causal=causal, active=True, scale=scale, impl=self.attn_impl, grad_sink=sink)
+        if self._fused_ok():
+            lin = self.log_Z1_lin[layer_idx]
+            sink = self.grad_sinks[layer_idx] if self.grad_sinks is not None else None
+            return ops.shifted_attention(q, k, v, self.attn_shift[layer_idx], lin.weight, lin.bias, key_mask,
+                                         causal=causal, active=True, scale=scale, impl=self.attn_impl, grad_sink=sink)
+        B, H, T, d = q.shape
+        shift = self.attn_shift[layer_idx].reshape(H, d)
+        if ShiftStrategy.LEARNABLE_SHIFT_SCALE not in self.attn_strategy:
+            # out = SA + shift (src/shift_encoder.py:717-729), per head or over the flat hidden dimension alike
+            sa = ops.shifted_attention(q, k, v, None, None, None, key_mask, causal=causal, active=False,
+                                       scale=scale, impl=self.attn_impl)
+            return (sa + shift).to(sa.dtype)
+        if ShiftStrategy.MULTI_HEAD in self.attn_strategy:       # LEARNABLE_SHIFT_SCALE without VECTOR_SHIFT never
+            raise NotImplementedError(repr(self.attn_strategy))   # activates a handle (register_shift_hooks)
+        sa, lse_full = ops.attention_with_full_lse(q, k, v, key_mask, causal=causal, scale=scale, impl=self.attn_impl)
+        mu = self._single_head_mu(layer_idx, q, lse_full)                       # [B,T,1]
+        return (sa + mu.unsqueeze(-1) * shift).to(sa.dtype)
 
     def do_shift(self, layer_idx, query_states, key_states, attn_output):
         """API-parity entry (src/shift_encoder.py:682-732): attn_output [B,T,H,d] + mu(q,K) * shift.
-        The mu term comes from the same fused kernel run with zero values, so that
-        SA == 0 and the kernel returns exactly mu * shift."""
+        The mu term comes from the same fused kernel run with zero values, so that SA == 0 and the kernel returns
+        exactly mu * shift (or, for the head-averaged variant, the unmasked log-sum-exp mu is formed from).
+        Like the reference, the non-MULTI_HEAD variants return [B,T,D]."""
         if not self.attn_shift_handles[layer_idx].active:
             return attn_output
-        if not self._fused_ok():
-            raise NotImplementedError("do_shift: only the mimic.yaml strategy is on the CUDA path")
-        lin = self.log_Z1_lin[layer_idx]
+        B, H, T, d = query_states.shape
+        scale = 1.0 / (self.lmm_hidden_dim // self.lmm_num_head) ** 0.5
+        multi = ShiftStrategy.MULTI_HEAD in self.attn_strategy
+        if not hasattr(self, "attn_shift"):
+            return attn_output if multi else attn_output.reshape(B, T, -1)
+        if not multi:
+            attn_output = attn_output.reshape(B, T, -1)
+        if ShiftStrategy.LEARNABLE_SHIFT_SCALE not in self.attn_strategy:
+            return attn_output + self.attn_shift[layer_idx][None, None, :]
         zeros_v = torch.zeros_like(key_states)
-        term = ops.shifted_attention(query_states, key_states, zeros_v, self.attn_shift[layer_idx], lin.weight,
-                                     lin.bias, None, causal=False, active=True,
-                                     scale=1.0 / (self.lmm_hidden_dim // self.lmm_num_head) ** 0.5,
-                                     impl=self.attn_impl)
-        return attn_output + term.to(attn_output.dtype)
+        if multi:
+            lin = self.log_Z1_lin[layer_idx]
+            term = ops.shifted_attention(query_states, key_states, zeros_v, self.attn_shift[layer_idx], lin.weight,
+                                         lin.bias, None, causal=False, active=True, scale=scale, impl=self.attn_impl)
+            return attn_output + term.to(attn_output.dtype)
+        _, lse_full = ops.attention_with_full_lse(query_states, key_states, zeros_v, None, causal=False, scale=scale,
+                                                  impl=self.attn_impl)
+        mu = self._single_head_mu(layer_idx, query_states, lse_full)
+        return attn_output + mu * self.attn_shift[layer_idx][None, None, :]

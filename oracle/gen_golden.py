@@ -57,7 +57,7 @@ def key_mask_for(case, B, S):
     return km
 
 
-def run_attn_case(case, seed):
+def run_attn_case(case, seed, strategy=None):
     se = ref_loader.load_shift_encoder()
     name, B, H, Hkv, T, S, d, causal, _l, _r, active, multi_head = case
     g = torch.Generator().manual_seed(seed)
@@ -65,13 +65,15 @@ def run_attn_case(case, seed):
     k = torch.randn(B, Hkv, S, d, generator=g)
     v = torch.randn(B, Hkv, S, d, generator=g)
     d_out = torch.randn(B, T, H, d, generator=g)
-    strategy = ref_loader.MIMIC_ATTN if multi_head else \
-        "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE"
+    if strategy is None:
+        strategy = ref_loader.MIMIC_ATTN if multi_head else \
+            "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE"
     enc = ref_loader.make_ref_encoder(H * d, 2, H, attn_strategy=strategy)
+    has_lin = hasattr(enc, "log_Z1_lin")        # absent without LEARNABLE_SHIFT_SCALE (out = attn + shift, 717-729)
     layer = 1
     with torch.no_grad():                       # "trained-like" values so mu is not ~0
         enc.attn_shift.copy_(torch.randn(enc.attn_shift.shape, generator=g) * 0.5)
-        for lin in enc.log_Z1_lin:
+        for lin in (enc.log_Z1_lin if has_lin else []):
             lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.2)
             lin.bias.copy_(torch.randn(lin.bias.shape, generator=g))
     enc.attn_shift_handles[layer].active = active
@@ -98,17 +100,20 @@ def run_attn_case(case, seed):
     out = enc.do_shift(layer, q_, kk, attn_t)   # THE reference call
     out = out.reshape(B, T, H, d)
     d_out = d_out * row_valid[:, :, None, None]  # fully-masked rows never reach a loss
-    params = [enc.attn_shift] + [p for p in enc.log_Z1_lin[layer].parameters()]
+    params = [enc.attn_shift] + ([p for p in enc.log_Z1_lin[layer].parameters()] if has_lin else [])
     grads = torch.autograd.grad(out, [q_, k_, v_] + params, d_out, allow_unused=True)
-    dq, dk, dv, dshift_all, dw, db = grads
+    dq, dk, dv, dshift_all = grads[:4]
     rec = dict(
         q=q, k=k, v=v, d_out=d_out, key_mask=km, row_valid=row_valid,
-        shift=enc.attn_shift[layer].detach().reshape(-1), w=enc.log_Z1_lin[layer].weight.detach(),
-        b=enc.log_Z1_lin[layer].bias.detach(), out=out.detach(), dq=dq, dk=dk, dv=dv,
+        shift=enc.attn_shift[layer].detach().reshape(-1), out=out.detach(), dq=dq, dk=dk, dv=dv,
         meta=np.array([B, H, Hkv, T, S, d, int(causal), int(active), int(multi_head)], dtype=np.int64),
     )
+    if has_lin:
+        rec.update(w=enc.log_Z1_lin[layer].weight.detach(), b=enc.log_Z1_lin[layer].bias.detach())
     if active:
-        rec.update(dshift=dshift_all[layer].reshape(-1), dw=dw, db=db)
+        rec.update(dshift=dshift_all[layer].reshape(-1))
+        if has_lin:
+            rec.update(dw=grads[4], db=grads[5])
     return {k_: (v_.numpy() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in rec.items()}
 
 
@@ -117,6 +122,68 @@ def gen_attention():
         rec = run_attn_case(case, 3407 + i)
         np.savez_compressed(os.path.join(OUT, f"attn_{case[0]}.npz"), **rec)
         print("attn", case[0], "out-norm", float(np.linalg.norm(rec["out"])))
+
+
+# ---------------------------------------------------------------- other encoder variants
+_V, _L, _M = "ShiftStrategy.VECTOR_SHIFT", "ShiftStrategy.LEARNABLE_SHIFT_SCALE", "ShiftStrategy.MULTI_HEAD"
+VARIANT_CASES = [
+    # attention-side variants of AttnApproximator.do_shift: key prefix, case tuple (ATTN_CASES layout), strategy string
+    ("sh_pad",    ("", 2, 4, 2, 40, 40, 32, True, [0, 7], None, True, False), f"{_V} | {_L}"),   # head-averaged mu, pads, GQA
+    ("sh_cache",  ("", 2, 4, 4, 6, 37, 32, True, None, None, True, False), f"{_V} | {_L}"),      # ... with T < S
+    ("vec_multi", ("", 2, 4, 4, 24, 24, 32, True, None, None, True, True), f"{_V} | {_M}"),      # out = attn + shift[h]
+    ("vec_flat",  ("", 2, 4, 4, 24, 24, 32, True, None, None, True, False), _V),                 # out = attn + shift
+]
+
+
+def gen_variants():
+    """tests/golden/variants.npz: the AttnApproximator strategies other than mimic.yaml's, the norm-preserving shift
+    hook of AttnFFNShift (src/shift_encoder.py:222-247) and of AttnApproximator's FFN hook (653-672), all produced by
+    calling the reference's own methods."""
+    se = ref_loader.load_shift_encoder()
+    rec = {}
+    for i, (key, case, strategy) in enumerate(VARIANT_CASES):
+        r = run_attn_case(case, 4407 + i, strategy=strategy)
+        rec.update({f"{key}.{k_}": v_ for k_, v_ in r.items()})
+        print("variant", key, "out-norm", float(np.linalg.norm(r["out"])))
+
+    g = torch.Generator().manual_seed(5407)
+    D, L = 256, 3
+    enc = se.AttnFFNShift(ref_loader.make_fake_lmm(D, L, 8), attn_strategy=f"{_V} | {_L}", ffn_strategy=_V,
+                          shift_scale_init_value=0.1)
+    with torch.no_grad():                                   # trained-like: the shift is visible next to h ~ N(0,1)
+        enc.attn_shift.copy_(torch.randn(L, D, generator=g) * 0.8)
+        enc.ffn_shift.copy_(torch.randn(L, D, generator=g) * 0.3)
+        enc.attn_shift_scale.copy_(torch.tensor([0.1, 0.7, -0.4]))
+    for prefix, layer in (("attn", 1), ("ffn", 2)):
+        h = torch.randn(2, 9, D, generator=g).requires_grad_(True)
+        dy = torch.randn(2, 9, D, generator=g)
+        hook = enc._shift_hook(prefix)
+        y, rest = hook(None, None, (h, "rest"), module_name=f"model.text_model.layers.{layer}.{prefix}")
+        assert rest == "rest"
+        shift, scale = getattr(enc, f"{prefix}_shift"), getattr(enc, f"{prefix}_shift_scale")
+        leaves = [h, shift] + ([scale] if scale.requires_grad else [])
+        grads = torch.autograd.grad(y, leaves, dy)
+        rec.update({f"ns_{prefix}.h": h.detach(), f"ns_{prefix}.dy": dy, f"ns_{prefix}.shift": shift[layer].detach(),
+                    f"ns_{prefix}.scale": scale[layer].detach(), f"ns_{prefix}.y": y.detach(),
+                    f"ns_{prefix}.dh": grads[0], f"ns_{prefix}.dshift": grads[1][layer]})
+        if scale.requires_grad:
+            rec[f"ns_{prefix}.dscale"] = grads[2][layer]
+    # AttnApproximator's FFN hook: same arithmetic, scale fixed at 1 (src/shift_encoder.py:661-667)
+    enc2 = ref_loader.make_ref_encoder(D, L, 8, ffn_strategy=f"{_V} | ShiftStrategy.RECORD_HIDDEN_STATES")
+    with torch.no_grad():
+        enc2.ffn_shift.copy_(torch.randn(L, D, generator=g) * 0.5)
+    captured = {}
+    enc2.lmm.register_forward_hook = lambda target, fn: captured.setdefault("hook", fn)
+    enc2.lmm.replace_module_method = lambda *a, **k: None
+    enc2.register_shift_hooks()
+    h = torch.randn(3, 5, D, generator=g).requires_grad_(True)
+    dy = torch.randn(3, 5, D, generator=g)
+    y = captured["hook"](None, None, h, module_name="model.text_model.layers.0.mlp")
+    grads = torch.autograd.grad(y, [h, enc2.ffn_shift], dy)
+    rec.update({"ns_approx.h": h.detach(), "ns_approx.dy": dy, "ns_approx.shift": enc2.ffn_shift[0].detach(),
+                "ns_approx.y": y.detach(), "ns_approx.dh": grads[0], "ns_approx.dshift": grads[1][0]})
+    rec = {k_: (v_.numpy() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in rec.items()}
+    np.savez_compressed(os.path.join(OUT, "variants.npz"), **rec)
 
 
 # ---------------------------------------------------------------- shift_model pieces
@@ -393,6 +460,58 @@ def gen_tiny_step_lora():
     print("tiny step + LoRA: loss", float(loss.detach()), "ce", float(ce.detach()), "mse", float(layer_loss["ffn_mse_loss"].detach()))
 
 
+def gen_tiny_step_licv():
+    """The LIVE baseline's step in miniature (config/encoder/licv.yaml: AttnFFNShift with a learnable, norm-preserving
+    FFN shift, scale init 0.1; Strategy.LM_LOSS | LOGITS_KL_DIV) through the reference's own hooks and loss methods."""
+    mb = ref_loader.load_model_base()
+    se = ref_loader.load_shift_encoder()
+    from torch import nn
+
+    class TinyLMM(mb.ModelBase):
+        def __init__(self, model):
+            nn.Module.__init__(self)
+            self.model = model
+            self.model_name = "llava-interleave-qwen-7b-hf"
+            self.config = model.config
+            self._trackers_dict = {}
+
+    lmm = TinyLMM(tiny_qwen2())
+    enc = se.AttnFFNShift(lmm, attn_strategy=None, ffn_strategy=f"{_V} | {_L}", shift_scale_init_value=0.1)
+    g = torch.Generator().manual_seed(4321)
+    with torch.no_grad():                              # trained-like: shift comparable to the MLP output norm
+        enc.ffn_shift.copy_(torch.randn(enc.ffn_shift.shape, generator=g) * 0.05)
+        enc.ffn_shift_scale.copy_(torch.tensor([0.1, 0.6, 1.3, -0.5]))
+    init = {k: v.detach().clone() for k, v in enc.state_dict().items() if not k.startswith("lmm")}
+    model, sm = make_ref_shift_model(enc, "Strategy.LM_LOSS | Strategy.LOGITS_KL_DIV")
+    full_ids, qa_ids = build_tiny_ids()
+    tok = _Tok()
+    hooks = enc.register_record_hooks()                # none: nothing is recorded under licv.yaml
+    assert not hooks
+    inputs = {"input_ids": full_ids, "attention_mask": full_ids != tok.pad_token_id}
+    q_inputs = {"input_ids": qa_ids, "attention_mask": qa_ids != tok.pad_token_id}
+    with torch.no_grad():
+        prefix_logits = lmm.model(**inputs)["logits"]
+    hooks.update(enc.register_shift_hooks())
+    assert set(hooks) == {"ffn_hook"} and len(hooks["ffn_hook"]) == 4
+    logits = lmm.model(**q_inputs)["logits"]
+    keep = q_inputs["attention_mask"][:, 1:]
+    ce = F.cross_entropy(logits[:, :-1][keep].float(), qa_ids[:, 1:][keep])
+    kl = model.calculate_logits_kl_loss(logits, prefix_logits, model.generate_label_mask(q_inputs, 1),
+                                        model.generate_label_mask(inputs, 2))
+    model.remove_hooks(hooks)
+    loss = 0.5 * ce + 1.0 * sum(kl.values())
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    assert set(params) == {"ffn_shift", "ffn_shift_scale"}
+    grads = torch.autograd.grad(loss, list(params.values()))
+    rec = {"full_ids": full_ids.numpy(), "qa_ids": qa_ids.numpy(), "loss": loss.detach().numpy(),
+           "ce_loss": ce.detach().numpy(), "logits_kl_loss": kl["logits_kl_loss"].detach().numpy()}
+    for (n, p), gr in zip(params.items(), grads):
+        rec["init." + n] = init[n].numpy()
+        rec["grad." + n] = gr.numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_step_licv.npz"), **rec)
+    print("tiny step (licv): loss", float(loss), "ce", float(ce), "kl", float(kl["logits_kl_loss"]))
+
+
 def main():
     assert ref_loader.available(), "reference tree not found; golden vectors can only be made where it is"
     os.makedirs(OUT, exist_ok=True)
@@ -401,6 +520,8 @@ def main():
     gen_loss_pieces()
     gen_tiny_step_lora()
     gen_tiny_step()
+    gen_variants()
+    gen_tiny_step_licv()
 
 
 if __name__ == "__main__":

@@ -71,7 +71,7 @@ def masked_attention(q, k, v, vis, scale) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def do_shift(q, k, attn_output, attn_shift_l, w_l, b_l, head_dim: Optional[int] = None,
-             multi_head: bool = True, active: bool = True):
+             multi_head: bool = True, active: bool = True, learnable_scale: bool = True):
     """Restatement of AttnApproximator.do_shift (src/shift_encoder.py:682-732).
 
     q [B,H,T,d], k [B,H,S,d] (post-RoPE, post-repeat_kv), attn_output [B,T,H,d].
@@ -88,6 +88,8 @@ def do_shift(q, k, attn_output, attn_shift_l, w_l, b_l, head_dim: Optional[int] 
     if not multi_head:                                 # lines 689-692
         q_t = q_t.reshape(B, T, -1)
         attn_output = attn_output.reshape(B, T, -1)
+    if not learnable_scale:                            # lines 717-729: VECTOR_SHIFT alone adds the bare vector
+        return attn_output + attn_shift_l[None, None, :]
     # lines 697-703: UNMASKED log-sum-exp over keys
     log_z2 = torch.logsumexp(torch.matmul(q, k.transpose(-2, -1)) / (head_dim ** 0.5), dim=-1).transpose(-2, -1)
     if not multi_head:                                 # lines 705-707

@@ -46,7 +46,7 @@ def test_attention_matches_reference_golden(path, dtype):
     g = load(path)
     B, H, Hkv, T, S, d, causal, active, multi_head = [int(x) for x in g["meta"]]
     if not multi_head:
-        pytest.skip("single-head mu variant is not on the CUDA path (mimic.yaml uses MULTI_HEAD)")
+        pytest.skip("head-averaged mu goes through the encoder, not the raw op: tests/test_gpu_variants.py")
     tol = TOL[dtype]
     # bf16: the kernel sees bf16-rounded inputs; compare with the oracle on the same rounded inputs
     # and, for fp32, directly with what the reference itself produced.

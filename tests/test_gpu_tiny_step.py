@@ -132,3 +132,34 @@ def test_tiny_step_matches_reference():
         assert rel(g, z["grad." + n]) < 2e-4, n
     # handles are inactive again, hooks removed (src/shift_model.py:262)
     assert not any(h.active for h in enc.attn_shift_handles)
+
+
+def test_tiny_step_licv_matches_reference():
+    """The LIVE baseline in miniature (src/config/encoder/licv.yaml: AttnFFNShift, learnable norm-preserving FFN shift,
+    Strategy.LM_LOSS | LOGITS_KL_DIV): loss terms and the gradients of ffn_shift / ffn_shift_scale against what the
+    reference produced through its own hooks (tests/golden/tiny_step_licv.npz)."""
+    from oracle.gen_golden import _Tok, tiny_qwen2
+    from mimic_b200 import AttnFFNShift, HookedModel, ShiftModel, Strategy, ops
+    z = np.load(os.path.join(GOLDEN, "tiny_step_licv.npz"))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lmm = HookedModel(tiny_qwen2().cuda(), "llava-interleave-qwen-7b-hf", processor=types.SimpleNamespace(tokenizer=_Tok()))
+    enc = AttnFFNShift(lmm, None, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE",
+                       shift_scale_init_value=0.1).cuda()
+    assert set(n for n, p in enc.named_parameters() if not n.startswith("lmm")) == {"ffn_shift", "ffn_shift_scale"}
+    assert float(enc.ffn_shift_scale[0]) == pytest.approx(0.1)
+    enc.load_state_dict({k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}, strict=False)
+    cfg = types.SimpleNamespace(ce_loss_weight=0.5, align_loss_weight=1.0,
+                                data=types.SimpleNamespace(num_image_in_query=1))
+    sm = ShiftModel(cfg, enc, Strategy.LM_LOSS | Strategy.LOGITS_KL_DIV)
+    full_ids, qa_ids = torch.from_numpy(z["full_ids"]).cuda(), torch.from_numpy(z["qa_ids"]).cuda()
+    n0 = ops.launch_count
+    loss_dict = sm.forward_inputs({"input_ids": full_ids}, {"input_ids": qa_ids})
+    assert set(loss_dict) == {"loss", "ce_loss", "logits_kl_loss"}
+    assert abs(float(loss_dict["ce_loss"]) - float(z["ce_loss"])) < 2e-5 * float(z["ce_loss"])
+    assert abs(float(loss_dict["logits_kl_loss"]) - float(z["logits_kl_loss"])) < 1e-3 * float(z["logits_kl_loss"])
+    assert abs(float(loss_dict["loss"]) - float(z["loss"])) < 2e-5 * float(z["loss"])
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    grads = torch.autograd.grad(loss_dict["loss"], list(params.values()))
+    assert ops.launch_count - n0 >= 4 + 4 + 2                 # 4 hook launches each way, CE and KL
+    for (n, p), g in zip(params.items(), grads):
+        assert rel(g, z["grad." + n]) < 2e-4, n

@@ -154,3 +154,60 @@ def test_lm_ce_rule():
                 tgt.append(ids[b, t + 1])
     want = torch.nn.functional.cross_entropy(torch.stack(rows), torch.stack(tgt))
     assert abs(float(got) - float(want)) < 1e-6
+
+
+# ---------------------------------------------------------------- other encoder variants
+VARIANTS = [("sh_pad", False, True), ("sh_cache", False, True), ("vec_multi", True, False), ("vec_flat", False, False)]
+
+
+def _variant(prefix):
+    z = np.load(os.path.join(GOLDEN, "variants.npz"))
+    return {k[len(prefix) + 1:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + ".")}
+
+
+@pytest.mark.parametrize("key,multi_head,learnable", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_do_shift_variants_oracle_matches_reference(key, multi_head, learnable):
+    """Head-averaged mu (src/shift_encoder.py:689-692, 705-707) and the bare vector shift (717-729): forward against
+    what the reference produced, autograd of the restatement against the reference's gradients."""
+    g = _variant(key)
+    B, H, Hkv, T, S, d, causal, active, mh = [int(x) for x in g["meta"]]
+    assert bool(mh) == multi_head and ("w" in g) == learnable
+    km, rv = g["key_mask"].bool(), g["row_valid"].bool()
+    q, k, v = (g[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+    shift = g["shift"].clone().requires_grad_(True)
+    w = g["w"].clone().requires_grad_(True) if learnable else None
+    b = g["b"].clone().requires_grad_(True) if learnable else None
+    kk, vv = OA.repeat_kv(k, H // Hkv), OA.repeat_kv(v, H // Hkv)
+    sa, _ = OA.masked_attention(q, kk, vv, OA.visibility(T, S, B, bool(causal), km), d ** -0.5)
+    sh = shift.view(H, d) if multi_head else shift
+    out = OA.do_shift(q, kk, sa.transpose(1, 2), sh, w, b, multi_head=multi_head, learnable_scale=learnable)
+    out = out.reshape(B, T, H, d)
+    m = rv[:, :, None, None].expand_as(g["out"])
+    assert rel(out[m], g["out"][m]) < 2e-6
+    leaves = [q, k, v, shift] + ([w, b] if learnable else [])
+    names = ["dq", "dk", "dv", "dshift"] + (["dw", "db"] if learnable else [])
+    for name, got in zip(names, torch.autograd.grad(out, leaves, g["d_out"])):
+        assert rel(got.reshape(g[name].shape), g[name]) < 5e-6, name
+
+
+@pytest.mark.parametrize("key", ["ns_attn", "ns_ffn", "ns_approx"])
+def test_norm_shift_oracle_matches_reference(key):
+    """AttnFFNShift._shift_hook (src/shift_encoder.py:233-240) / AttnApproximator's FFN hook (661-667)."""
+    from oracle import norm_shift as NS
+    g = _variant(key)
+    scale = g["scale"] if "scale" in g else torch.tensor(1.0)
+    y = NS.norm_shift_fwd(g["h"], g["shift"], scale)
+    assert rel(y, g["y"]) < 1e-6
+    # norm preserved per token row
+    assert torch.allclose(y.norm(dim=-1), g["h"].norm(dim=-1), rtol=1e-5)
+    dh, dshift, dscale = NS.norm_shift_bwd(g["h"], g["shift"], scale, g["dy"])
+    assert rel(dh, g["dh"]) < 5e-6
+    assert rel(dshift, g["dshift"]) < 5e-6
+    if "dscale" in g:
+        assert rel(dscale, g["dscale"]) < 5e-6
+    # closed form == autograd of the forward restatement, fp64
+    h, sh, sc = g["h"].double().requires_grad_(True), g["shift"].double().requires_grad_(True), scale.double().requires_grad_(True)
+    ag = torch.autograd.grad(NS.norm_shift_fwd(h, sh, sc), [h, sh, sc], g["dy"].double())
+    ex = NS.norm_shift_bwd(h.detach(), sh.detach(), sc.detach(), g["dy"].double())
+    for a_, e_ in zip(ag, ex):
+        assert rel(e_, a_) < 1e-12
