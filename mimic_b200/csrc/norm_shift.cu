@@ -43,6 +43,38 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// 8 consecutive elements as loaded, unpacked to fp32 only when the row is processed: the NEXT row's loads are issued
+// before the current row's reduction, so a CTA always has a row in flight (one row per CTA at a time left the backward
+// at 0.28 of HBM peak)
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = ldg_stream(p); }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  uint4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = ldg_stream(p);
+    b = ldg_stream(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+    f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+  }
+};
+
 // VEC 8-element vectors per thread: D <= NS_THREADS * 8 * VEC
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NS_THREADS) norm_shift_fwd_kernel(const T* __restrict__ h, int64_t h_stride,
@@ -59,15 +91,33 @@ __global__ void __launch_bounds__(NS_THREADS) norm_shift_fwd_kernel(const T* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) sv[i][e] = j < nvec ? s * shift[8 * j + e] : 0.f;
   }
+  Raw8<T> nh[VEC];
+  if (blockIdx.x < N) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = threadIdx.x + NS_THREADS * i;
+      if (j < nvec) nh[i].load(h + (int64_t)blockIdx.x * h_stride + 8 * j);
+    }
+  }
   for (int row = blockIdx.x; row < N; row += gridDim.x) {
-    const T* hr = h + (int64_t)row * h_stride;
     float u[VEC][8];
     float hh = 0.f, uu = 0.f, unused = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int j = threadIdx.x + NS_THREADS * i;
+      if (j < nvec) nh[i].unpack(u[i]);
+    }
+    if (row + (int)gridDim.x < N) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int j = threadIdx.x + NS_THREADS * i;
+        if (j < nvec) nh[i].load(h + (int64_t)(row + gridDim.x) * h_stride + 8 * j);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = threadIdx.x + NS_THREADS * i;
       if (j < nvec) {
-        load8(hr + 8 * j, u[i]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           hh += u[i][e] * u[i][e];
@@ -111,17 +161,42 @@ __global__ void __launch_bounds__(NS_THREADS) norm_shift_bwd_kernel(const T* __r
       gacc[i][e] = 0.f;
     }
   }
+  Raw8<T> nh[VEC], ng[VEC];
+  if (blockIdx.x < N) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = threadIdx.x + NS_THREADS * i;
+      if (j < nvec) {
+        nh[i].load(h + (int64_t)blockIdx.x * h_stride + 8 * j);
+        ng[i].load(dy + (int64_t)blockIdx.x * dy_stride + 8 * j);
+      }
+    }
+  }
   for (int row = blockIdx.x; row < N; row += gridDim.x) {
-    const T* hr = h + (int64_t)row * h_stride;
-    const T* gr = dy + (int64_t)row * dy_stride;
     float hv[VEC][8], gv[VEC][8];
     float hh = 0.f, uu = 0.f, pu = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int j = threadIdx.x + NS_THREADS * i;
       if (j < nvec) {
-        load8(hr + 8 * j, hv[i]);
-        load8(gr + 8 * j, gv[i]);
+        nh[i].unpack(hv[i]);
+        ng[i].unpack(gv[i]);
+      }
+    }
+    if (row + (int)gridDim.x < N) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int j = threadIdx.x + NS_THREADS * i;
+        if (j < nvec) {
+          nh[i].load(h + (int64_t)(row + gridDim.x) * h_stride + 8 * j);
+          ng[i].load(dy + (int64_t)(row + gridDim.x) * dy_stride + 8 * j);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = threadIdx.x + NS_THREADS * i;
+      if (j < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float uv = hv[i][e] + sv[i][e];
@@ -192,8 +267,8 @@ int launch_fwd(const void* h, int64_t hs, const float* shift, const float* scale
 template <typename T>
 int launch_bwd(const void* h, int64_t hs, const void* dy, int64_t gs, const float* shift, const float* scale, void* dh,
                float* gsum, int N, int D, cudaStream_t st) {
-  // the column sums leave each CTA as D/4 vector reductions: few CTAs with several rows each beat one CTA per row
-  const int grid = std::min(N, num_sms());
+  // the column sums leave each CTA as D/4 vector reductions at the end, so the grid is capped at what is resident
+  const int grid = std::min(N, 4 * num_sms());
   const T* hp = static_cast<const T*>(h);
   const T* gp = static_cast<const T*>(dy);
   T* dp = static_cast<T*>(dh);

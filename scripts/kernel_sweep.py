@@ -131,6 +131,31 @@ def ce(R, V):
     return {"R": R, "V": V, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
 
 
+def norm_shift(N, D):
+    """AttnFFNShift's hook body (src/shift_encoder.py:233-240): fwd 2*N*D*2 B, bwd 3*N*D*2 B; the reference's own
+    eager arithmetic on the same GPU beside it."""
+    h = torch.randn(N, D, device=dev).bfloat16().requires_grad_(True)
+    dy = torch.randn(N, D, device=dev).bfloat16()
+    shift = (torch.randn(D, device=dev) * 0.1).requires_grad_(True)
+    scale = torch.tensor(0.5, device=dev, requires_grad=True)
+
+    def fn():
+        y = ops.norm_shift(h, shift, scale)
+        torch.autograd.grad(y, [h, shift, scale], dy)
+    ms_f = time_kernel(fn, "norm_shift_fwd")
+    ms_b = time_kernel(fn, "norm_shift_bwd")
+
+    def ref():
+        shifted = h + scale * shift
+        y = shifted / shifted.norm(dim=-1, keepdim=True) * h.norm(dim=-1, keepdim=True)
+        torch.autograd.grad(y, [h, shift, scale], dy.float())
+    ms_ref = timeit(ref, flush=True)
+    nb = N * D * 2
+    return {"N": N, "D": D, "fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_gbs": 2 * nb / ms_f / 1e6, "bwd_gbs": 3 * nb / ms_b / 1e6,
+            "fwd_frac_of_hbm": 2 * nb / ms_f / 1e6 / PEAK["hbm_gbs"], "bwd_frac_of_hbm": 3 * nb / ms_b / 1e6 / PEAK["hbm_gbs"],
+            "reference_eager_fwd_bwd_ms": ms_ref, "speedup_vs_reference_eager": ms_ref / (ms_f + ms_b)}
+
+
 def gather(rows_src, N, D):
     src = torch.randn(rows_src, D, device=dev).bfloat16()
     idx = torch.randperm(rows_src, device=dev)[:N].sort().values.to(torch.int32)
@@ -143,13 +168,18 @@ def gather(rows_src, N, D):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     res = {"peaks": PEAK}
+    if which == "norm_shift":
+        res["norm_shift"] = [norm_shift(256, 4096), norm_shift(6400, 4096), norm_shift(65536, 4096)]
+        for r in res["norm_shift"]:
+            print("norm_shift", {a: (round(b, 4) if isinstance(b, float) else b) for a, b in r.items()}, flush=True)
     if which in ("all", "hbm"):
         res["mse"] = [mse(32, 256, 4096), mse(32, 4096, 4096)]
         res["ce"] = [ce(256, 32003), ce(1540, 152000)]
         res["gather"] = [gather(6400, 256, 4096), gather(65536, 16384, 4096)]
         res["cos"] = [cos(32, 256, 4096), cos(32, 4096, 4096)]
         res["kl"] = [kl(256, 32003), kl(1540, 152000)]
-        for k in ("mse", "cos", "ce", "kl", "gather"):
+        res["norm_shift"] = [norm_shift(256, 4096), norm_shift(6400, 4096), norm_shift(65536, 4096)]
+        for k in ("mse", "cos", "ce", "kl", "gather", "norm_shift"):
             for r in res[k]:
                 print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in r.items()}, flush=True)
     if which in ("all", "ref"):
