@@ -238,6 +238,15 @@ MIMIC_API int mimic_adamw_step(float* param, float* grad, float* exp_avg, float*
                      const float* weight_decay, int64_t n, const float* hyper, float beta1, float beta2,
                      float eps, float grad_mul, float max_norm, float* sumsq, void* stream);
 
+/* Same step with a per-element learning-rate multiplier lr_mul fp32 [n] (or NULL = all ones): the reference's optional
+ * second learning rate, cfg.peft.scale_lr, for parameters whose name contains "log_Z1" or "scale"
+ * (src/shift_model.py:341-355; "typically used for LIVE").  lr_mul[i] = scale_lr / lr for those, 1 elsewhere — the
+ * cosine-with-warm-up factor multiplies both groups alike (LambdaLR). */
+MIMIC_API int mimic_adamw_step_groups(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                     const float* weight_decay, const float* lr_mul, int64_t n, const float* hyper,
+                     float beta1, float beta2, float eps, float grad_mul, float max_norm, float* sumsq,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,8 @@ EXPORTS = {
     "mimic_ce_workspace": (C.c_size_t, [C.c_int32]),
     "mimic_ce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mimic_adamw_step_groups": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                                            C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "mimic_adamw_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
 }

@@ -1028,8 +1028,9 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ gra
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                                                     float* __restrict__ v, const float* __restrict__ wd, int64_t n,
                                                     const float* __restrict__ hyper, float beta1, float beta2, float eps,
-                                                    float max_norm, const float* __restrict__ sumsq) {
-  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
+                                                    float max_norm, const float* __restrict__ sumsq,
+                                                    const float* __restrict__ lr_mul) {
+  const float lr0 = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
   float clip = 1.f;
   if (max_norm > 0.f) {
     const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);   // torch.nn.utils.clip_grad_norm_
@@ -1037,6 +1038,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, c
   }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float g = grad[i] * clip;
+    const float lr = lr_mul ? lr0 * lr_mul[i] : lr0;   // second learning rate of the reference's scale group
     float p = param[i];
     p *= 1.f - lr * wd[i];
     const float mi = beta1 * m[i] + (1.f - beta1) * g;
@@ -1273,6 +1275,14 @@ extern "C" int mimic_rope_qk(const void* q, int64_t q_sb, int64_t q_st, int64_t 
 extern "C" int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* weight_decay,
                                 int64_t n, const float* hyper, float beta1, float beta2, float eps, float grad_mul,
                                 float max_norm, float* sumsq, void* stream) {
+  return mimic_adamw_step_groups(param, grad, exp_avg, exp_avg_sq, weight_decay, nullptr, n, hyper, beta1, beta2, eps,
+                                 grad_mul, max_norm, sumsq, stream);
+}
+
+extern "C" int mimic_adamw_step_groups(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                       const float* weight_decay, const float* lr_mul, int64_t n, const float* hyper,
+                                       float beta1, float beta2, float eps, float grad_mul, float max_norm, float* sumsq,
+                                       void* stream) {
   MIMIC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && weight_decay && hyper && sumsq, "NULL argument");
   MIMIC_CHECK_ARG(n > 0, "bad n");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1280,7 +1290,8 @@ extern "C" int mimic_adamw_step(float* param, float* grad, float* exp_avg, float
   const int grid = (int)((n + 255) / 256 < (int64_t)num_sms() * 4 ? (n + 255) / 256 : (int64_t)num_sms() * 4);
   grad_sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_mul, sumsq);
   MIMIC_LAUNCH_OK("grad_sumsq_kernel");
-  adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, weight_decay, n, hyper, beta1, beta2, eps, max_norm, sumsq);
+  adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, weight_decay, n, hyper, beta1, beta2, eps, max_norm, sumsq,
+                                     lr_mul);
   MIMIC_LAUNCH_OK("adamw_kernel");
   return MIMIC_OK;
 }

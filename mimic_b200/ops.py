@@ -565,13 +565,16 @@ def adamw_hyper(lr: float, step: int, betas=(0.9, 0.999)) -> torch.Tensor:
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper: torch.Tensor, *, betas=(0.9, 0.999),
-               eps=1e-8, grad_mul=1.0, max_norm=0.0, sumsq: Optional[torch.Tensor] = None) -> None:
+               eps=1e-8, grad_mul=1.0, max_norm=0.0, sumsq: Optional[torch.Tensor] = None,
+               lr_mul: Optional[torch.Tensor] = None) -> None:
     """Clip (global norm) + AdamW on flat fp32 buffers, on device (replaces DeepSpeedCPUAdam).
-    hyper: device fp32 [3] = adamw_hyper(lr, step) (device-resident so a CUDA graph can replay the step)."""
-    _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper)
+    hyper: device fp32 [3] = adamw_hyper(lr, step) (device-resident so a CUDA graph can replay the step).
+    lr_mul: optional fp32 [n] per-element learning-rate multiplier (the reference's scale_lr group)."""
+    _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper, lr_mul)
     if sumsq is None:
         sumsq = torch.empty(1, dtype=torch.float32, device=param.device)
-    check(lib.mimic_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(weight_decay),
-                               param.numel(), _ptr(hyper), betas[0], betas[1], eps, float(grad_mul),
-                               float(max_norm), _ptr(sumsq), _stream()), "mimic_adamw_step")
+    check(lib.mimic_adamw_step_groups(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(weight_decay),
+                                      _ptr(lr_mul), param.numel(), _ptr(hyper), betas[0], betas[1], eps,
+                                      float(grad_mul), float(max_norm), _ptr(sumsq), _stream()),
+          "mimic_adamw_step_groups")
     _count(2)

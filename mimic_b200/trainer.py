@@ -25,7 +25,8 @@ from .shift_model import ShiftModel
 
 
 class FlatShiftParams:
-    def __init__(self, encoder, weight_decay: float, n_scalars: int = 4):
+    def __init__(self, encoder, weight_decay: float, n_scalars: int = 4, lr: float = 1.0,
+                 scale_lr: Optional[float] = None):
         # every trainable parameter reachable from the encoder: the shift parameters and — the backbone being a
         # sub-module (`encoder.lmm`) — any LoRA adapter weights, like the reference's optimizer (src/shift_model.py:338-340)
         named = [(n, p) for n, p in encoder.named_parameters() if p.requires_grad]
@@ -43,6 +44,8 @@ class FlatShiftParams:
         self.weight_decay = torch.empty(self.numel, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.param)
         self.exp_avg_sq = torch.zeros_like(self.param)
+        # cfg.peft.scale_lr (src/shift_model.py:341-355): names containing "log_Z1" or "scale" train at scale_lr
+        self.lr_mul = torch.ones(self.numel, dtype=torch.float32, device=dev) if scale_lr else None
         self.views: Dict[str, torch.Tensor] = {}
         off = 0
         for n, p in named:
@@ -53,6 +56,8 @@ class FlatShiftParams:
             p.grad = g
             self.views[n] = g
             self.weight_decay[off:off + k] = 0.0 if "bias" in n else weight_decay      # shift_model.py:309
+            if self.lr_mul is not None and ("log_Z1" in n or "scale" in n):
+                self.lr_mul[off:off + k] = scale_lr / lr
             off += k
         # per-layer sinks for the fused attention backward
         if hasattr(encoder, "attn_shift") and hasattr(encoder, "log_Z1_lin") and encoder._fused_ok():
@@ -73,10 +78,10 @@ def cosine_with_warmup(step: int, warmup: int, total: int) -> float:
 class MimicTrainer:
     def __init__(self, shift_model: ShiftModel, *, lr: float = 5e-3, weight_decay: float = 1e-3, warmup_step=0.1,
                  total_steps: int = 1000, grad_clip_val: float = 1.0, accumulate_grad_batches: int = 1,
-                 process_group=None):
+                 process_group=None, scale_lr: Optional[float] = None):
         self.sm = shift_model
         self.sm.check_separators = False            # no host sync inside the step
-        self.flat = FlatShiftParams(shift_model.shift_encoder, weight_decay)
+        self.flat = FlatShiftParams(shift_model.shift_encoder, weight_decay, lr=lr, scale_lr=scale_lr)
         self.base_lr, self.total_steps = lr, total_steps
         self.warmup = int(warmup_step * total_steps) if isinstance(warmup_step, float) else int(warmup_step)
         self.clip = grad_clip_val
@@ -129,7 +134,7 @@ class MimicTrainer:
             dist.all_reduce(self.flat.grad_and_scalars, group=self.pg)      # the only collective of the path
         ops.adamw_step(self.flat.param, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq,
                        self.flat.weight_decay, self.hyper, grad_mul=1.0 / self.world,
-                       max_norm=self.clip, sumsq=self.sumsq)
+                       max_norm=self.clip, sumsq=self.sumsq, lr_mul=self.flat.lr_mul)
 
     def optimizer_step(self) -> None:
         with self._on_stream():

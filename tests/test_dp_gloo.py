@@ -15,16 +15,17 @@ MIMIC = ("ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | Shi
 
 
 def _adamw_torch(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper, *, betas=(0.9, 0.999), eps=1e-8, grad_mul=1.0,
-                 max_norm=0.0, sumsq=None):
-    """torch restatement of mimic_adamw_step (clip + AdamW), test-only."""
+                 max_norm=0.0, sumsq=None, lr_mul=None):
+    """torch restatement of mimic_adamw_step[_groups] (clip + AdamW), test-only."""
     lr, bc1, bc2s = [float(x) for x in hyper]
+    lr = lr * (lr_mul if lr_mul is not None else torch.ones_like(param))
     grad.mul_(grad_mul)
     if max_norm > 0:
         grad.mul_(min(1.0, max_norm / (float(grad.norm()) + 1e-6)))
     param.mul_(1 - lr * weight_decay)
     exp_avg.mul_(betas[0]).add_(grad, alpha=1 - betas[0])
     exp_avg_sq.mul_(betas[1]).addcmul_(grad, grad, value=1 - betas[1])
-    param.addcdiv_(exp_avg, exp_avg_sq.sqrt() / bc2s + eps, value=-lr / bc1)
+    param.sub_(lr / bc1 * exp_avg / (exp_avg_sq.sqrt() / bc2s + eps))
 
 
 def _make_trainer():

@@ -277,3 +277,41 @@ def test_adamw_step_matches_torch():
         want = torch.empty(n)
         want[wd == 0], want[wd != 0] = pa.detach(), pb.detach()
         assert rel(p, want) < 1e-6
+
+
+def test_adamw_scale_lr_group_matches_torch():
+    """cfg.peft.scale_lr (src/shift_model.py:341-355): parameters named *log_Z1* / *scale* train at a second learning
+    rate; four torch param groups (bias / non-bias x regular / scale) against the flat buffer with per-element vectors."""
+    from mimic_b200 import ops
+    torch.manual_seed(1)
+    n, lr, scale_lr = 4099, 5e-3, 1e-4
+    p0 = torch.randn(n)
+    idx = torch.arange(n)
+    no_decay, scaled = idx % 5 == 0, idx % 3 == 0
+    groups, masks = [], []
+    for nd in (True, False):
+        for sc in (True, False):
+            mk = (no_decay == nd) & (scaled == sc)
+            masks.append(mk)
+            groups.append({"params": [torch.nn.Parameter(p0[mk].clone())], "weight_decay": 0.0 if nd else 1e-3,
+                           "lr": scale_lr if sc else lr})
+    opt = torch.optim.AdamW(groups, lr=lr)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 0.5 ** s)       # one lambda for every group, like the reference
+    wd = torch.where(no_decay, torch.zeros(n), torch.full((n,), 1e-3)).cuda()
+    lr_mul = torch.where(scaled, torch.full((n,), scale_lr / lr), torch.ones(n)).cuda()
+    p = p0.clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        g = torch.randn(n) * 3
+        params = [gr["params"][0] for gr in groups]
+        for prm, mk in zip(params, masks):
+            prm.grad = g[mk].clone()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        ops.adamw_step(p, g.cuda(), m, v, wd, ops.adamw_hyper(lr * 0.5 ** (step - 1), step).cuda(), max_norm=1.0,
+                       lr_mul=lr_mul)
+        sched.step()
+        want = torch.empty(n)
+        for prm, mk in zip(params, masks):
+            want[mk] = prm.detach()
+        assert rel(p, want) < 1e-6

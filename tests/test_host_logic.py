@@ -276,3 +276,33 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout + run.stderr
+
+
+def test_flat_params_scale_lr_groups():
+    """FlatShiftParams: weight decay 0 for *bias* names, lr multiplier scale_lr / lr for *log_Z1* / *scale* names
+    (src/shift_model.py:306-357), for both encoder classes."""
+    from mimic_b200 import AttnApproximator, AttnFFNShift
+    from mimic_b200.trainer import FlatShiftParams
+    from oracle.ref_loader import make_fake_lmm
+    enc = AttnFFNShift(make_fake_lmm(64, 3, 4), None, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE",
+                       shift_scale_init_value=0.1)
+    assert {n for n, _ in enc.named_parameters()} == {"ffn_shift", "ffn_shift_scale"}
+    assert torch.allclose(enc.ffn_shift_scale, torch.full((3,), 0.1))
+    flat = FlatShiftParams(enc, 1e-3, lr=5e-3, scale_lr=1e-4)
+    assert flat.numel == 3 * 64 + 3
+    by_name = dict(zip(flat.names, torch.split(flat.lr_mul, [enc.get_parameter(n).numel() for n in flat.names])))
+    assert torch.all(by_name["ffn_shift"] == 1.0) and torch.allclose(by_name["ffn_shift_scale"], torch.tensor(0.02))
+    assert FlatShiftParams(enc, 1e-3).lr_mul is None
+    enc2 = AttnApproximator(make_fake_lmm(64, 2, 4),
+                            "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD", None)
+    flat2 = FlatShiftParams(enc2, 1e-3, lr=1e-2, scale_lr=1e-3)
+    sizes = [enc2.get_parameter(n).numel() for n in flat2.names]
+    for n, mul, wd in zip(flat2.names, torch.split(flat2.lr_mul, sizes), torch.split(flat2.weight_decay, sizes)):
+        assert torch.allclose(mul, torch.tensor(0.1 if "log_Z1" in n else 1.0)), n
+        assert torch.all(wd == (0.0 if "bias" in n else 1e-3)), n
+    # the other AttnFFNShift shapes: non-learnable scale is a buffer, MULTI_HEAD is refused like the reference does
+    enc3 = AttnFFNShift(make_fake_lmm(64, 3, 4), "ShiftStrategy.VECTOR_SHIFT", None)
+    assert {n for n, _ in enc3.named_parameters()} == {"attn_shift"} and "attn_shift_scale" in dict(enc3.named_buffers())
+    with pytest.raises(ValueError):
+        AttnFFNShift(make_fake_lmm(64, 3, 4), "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.MULTI_HEAD", None)
+    assert AttnFFNShift(make_fake_lmm(64, 3, 4), None, None).register_shift_hooks() == {}
