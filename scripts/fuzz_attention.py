@@ -52,7 +52,9 @@ def one(rng, idx):
             km[:, -1] = True
     sh, w, b = ((torch.randn(H, d, device="cuda", generator=g) * 0.5, torch.randn(H, d, device="cuda", generator=g) * 0.2,
                  torch.randn(H, device="cuda", generator=g)) if active else (None, None, None))
-    tag = f"#{idx} B{B} H{H}/{Hkv} T{T} S{S} causal{int(causal)} active{int(active)} pad{int(pad)}"
+    # a gradient arriving at lse_full from outside (head-averaged mu variant, mimic_shifted_attn_bwd_lse)
+    d_lse = torch.randn(B, H, T, device="cuda", generator=g) if (active and rng.random() < 0.4) else None
+    tag = f"#{idx} B{B} H{H}/{Hkv} T{T} S{S} causal{int(causal)} active{int(active)} pad{int(pad)} dlse{int(d_lse is not None)}"
     res = {}
     for impl in ("simt", "tcgen05"):
         out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, km, sh, w, b, causal=causal, active=active,
@@ -60,7 +62,7 @@ def one(rng, idx):
         # rows without any visible key are defined as SA = 0 and must not send gradient anywhere
         vis = torch.isfinite(lse_c).permute(0, 2, 1)[..., None]           # [B,T,H,1]
         grads = ops.shifted_attention_backward(saved, out, do * vis.to(do.dtype), lse_c, lse_f, mu, causal=causal, active=active,
-                                               scale=d ** -0.5, impl=impl)
+                                               scale=d ** -0.5, impl=impl, d_lse_full=d_lse)
         res[impl] = (out.float(), lse_c, lse_f, mu, grads)
     a, t = res["simt"], res["tcgen05"]
     errs = {"out": rel(t[0], a[0])}
