@@ -68,6 +68,17 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       if (tracing) p.trace[role * 8 + e] = clock64();
     }
   };
+  // steady-state view: the heaviest query tile of the last head / batch row (dispatched when every SM is busy) stamps
+  // steps of its key loop: trace[24 + 6 (j-8) + e], j = 8..11, e = softmax wait begin / S tile seen / scores in registers /
+  // row max + rescale decision / P stored (issued) / SOFT_DONE arrive;  trace[48 + 4 (j-8) + e] = issuer saw SOFT_DONE(j) /
+  // V(j) landed / PV(j) issued / K(j+2) landed (the QK^T(j+2) issue follows immediately)
+  const bool tracing_ss = DBG && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == gridDim.y - 1 &&
+                          blockIdx.z == gridDim.z - 1;
+  auto stamp_ss = [&](int base, int per, int j, int e) {
+    if constexpr (DBG) {
+      if (tracing_ss && j >= 8 && j < 12) p.trace[base + per * (j - 8) + e] = clock64();
+    }
+  };
   if (threadIdx.x == 0) stamp(0, 0);                   // CTA entry
   const int qt = gridDim.x - 1 - blockIdx.x;          // heaviest (latest) query tiles first
   const int h = blockIdx.y, b = blockIdx.z;
@@ -173,6 +184,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 210 + st);
+        if (lane == 0) stamp_ss(48, 4, j - 2, 3);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t k_lo = k_lo0 + st * (KV_TILE >> 4);
@@ -193,9 +205,11 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       for (int j = 0; j < n; ++j) {
         const int st = j & 1;
         mbar_wait(&bars[SOFT_DONE + st], (j >> 1) & 1, 220 + st);
+        if (lane == 0) stamp_ss(48, 4, j, 0);
         tc_fence_after();
         if (j <= jd) {
           mbar_wait(&bars[V_FULL + st], (j >> 1) & 1, 230 + st);
+          if (lane == 0) stamp_ss(48, 4, j, 1);
           tc_fence_after();
           if (elect_one()) {
             // A: P_j in TMEM (64 keys = 32 packed columns, 8 per K step); B: V_j [64 keys][d], 16 keys = 2 KB per step
@@ -215,6 +229,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tc_commit(&bars[PV_DONE]);
           }
           __syncwarp();
+          if (lane == 0) stamp_ss(48, 4, j, 2);
         }
         // QK^T(j+2) goes out as soon as S[st] is free.  (Measured: issuing the scores of two tiles together — which one
         // N=128 MMA series over both K stages would need, 517 instead of 2 x 389 cycles — gives up this one-step lookahead
@@ -258,7 +273,9 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     float m_c = -INFINITY, l_c = 0.f, m_x = -INFINITY, l_x = 0.f;   // log2 domain
     for (int j = 0; j < n; ++j) {
       const int st = j & 1;
+      if (str) stamp_ss(24, 6, j, 0);
       mbar_wait(&bars[S_FULL + st], (j >> 1) & 1, 310 + st);
+      if (str) stamp_ss(24, 6, j, 1);
       if (str && j == 0) stamp(2, 1);                   // first score tile
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + st * BN;
@@ -281,6 +298,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tmem_ld32(taddr, *reinterpret_cast<float(*)[32]>(s));
       tmem_ld32(taddr + 32, *reinterpret_cast<float(*)[32]>(s + 32));
       tc_wait_ld();
+      if (str) stamp_ss(24, 6, j, 2);
       if (j <= jd) {
         float mv = -INFINITY;
         if (all_vis) {
@@ -316,8 +334,10 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
         }
         const float neg_m = (m_c == -INFINITY) ? 0.f : -m_c;
+        if (str) stamp_ss(24, 6, j, 3);
         if (all_vis) {
           l_c += exp_pack_store64(s, scale2, neg_m, taddr);
+          if (str) stamp_ss(24, 6, j, 4);
         } else {
           float rowsum = 0.f;
 #pragma unroll
@@ -376,6 +396,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(&bars[SOFT_DONE + st]);
+      if (str) stamp_ss(24, 6, j, 5);
       if (str && j == 0) stamp(2, 2);                   // first softmax done
     }
     if (str) stamp(2, 3);                               // all steps done
