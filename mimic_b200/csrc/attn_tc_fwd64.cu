@@ -159,18 +159,25 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int j = NKV; j < n; ++j) {                    // tiles 0 .. NKV-1 were issued in the prologue
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 100 + st);
-        mbar_expect_tx(&bars[K_FULL + st], KV_TILE);
-        tma_load_4d(sK + st * KV_TILE, &tm_k, &bars[K_FULL + st], 0, j * BN, kvh, b);
-        tma_load_4d(sK + st * KV_TILE + KV_HALF, &tm_k, &bars[K_FULL + st], 64, j * BN, kvh, b);
-        if (j <= jd) {
-          mbar_wait(&bars[V_EMPTY + st], ph ^ 1, 110 + st);
-          mbar_expect_tx(&bars[V_FULL + st], KV_TILE);
-          tma_load_4d(sV + st * KV_TILE, &tm_v, &bars[V_FULL + st], 0, j * BN, kvh, b);
-          tma_load_4d(sV + st * KV_TILE + KV_HALF, &tm_v, &bars[V_FULL + st], 64, j * BN, kvh, b);
+      // Tiles 0 .. NKV-1 were issued in the prologue.  K runs one tile ahead of V, which is the order the stages free up
+      // in: the issuer's MMA stream is ... PV(j-3), QK^T(j-1), PV(j-2), QK^T(j) ..., so the stage of K(j+2) (freed by
+      // QK^T(j)) is available before the stage of V(j+1) (freed by PV(j-1)).  With K(j), V(j) requested together K(j+2)
+      // sat behind the wait for PV(j-1), a whole softmax step later than necessary.
+      for (int j = NKV; j <= n; ++j) {
+        if (j < n) {
+          const int st = j & 1;
+          mbar_wait(&bars[K_EMPTY + st], ((j >> 1) & 1) ^ 1, 100 + st);
+          mbar_expect_tx(&bars[K_FULL + st], KV_TILE);
+          tma_load_4d(sK + st * KV_TILE, &tm_k, &bars[K_FULL + st], 0, j * BN, kvh, b);
+          tma_load_4d(sK + st * KV_TILE + KV_HALF, &tm_k, &bars[K_FULL + st], 64, j * BN, kvh, b);
+        }
+        const int jv = j - 1;
+        if (jv >= NKV && jv <= jd) {
+          const int sv = jv & 1;
+          mbar_wait(&bars[V_EMPTY + sv], ((jv >> 1) & 1) ^ 1, 110 + sv);
+          mbar_expect_tx(&bars[V_FULL + sv], KV_TILE);
+          tma_load_4d(sV + sv * KV_TILE, &tm_v, &bars[V_FULL + sv], 0, jv * BN, kvh, b);
+          tma_load_4d(sV + sv * KV_TILE + KV_HALF, &tm_v, &bars[V_FULL + sv], 64, jv * BN, kvh, b);
         }
       }
     }
