@@ -249,6 +249,8 @@ class _NormShift(torch.autograd.Function):
         if h2.stride(-1) != 1 or h2.stride(0) % 8 or h2.data_ptr() % 16:
             h2 = h2.contiguous()
         sh = shift.detach().float().contiguous()
+        if sh.data_ptr() % 16:                 # a row of a parameter that sits at an odd offset of the flat optimizer buffer
+            sh = sh.clone()
         sc = None if scale is None else scale.detach().float().reshape(1).contiguous()
         y = torch.empty(h2.shape, dtype=h.dtype, device=h.device)
         if h2.shape[0]:

@@ -25,7 +25,7 @@ from .shift_model import ShiftModel
 
 
 class FlatShiftParams:
-    def __init__(self, encoder, weight_decay: float, n_scalars: int = 4, lr: float = 1.0,
+    def __init__(self, encoder, weight_decay: float, n_scalars: int = 8, lr: float = 1.0,
                  scale_lr: Optional[float] = None):
         # every trainable parameter reachable from the encoder: the shift parameters and — the backbone being a
         # sub-module (`encoder.lmm`) — any LoRA adapter weights, like the reference's optimizer (src/shift_model.py:338-340)
@@ -93,6 +93,8 @@ class MimicTrainer:
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.opt_step = 0
         self.micro = 0
+        self._scalar_keys = ["loss", "ce_loss", "ffn_mse_loss"]     # slots at the tail of the all-reduce buffer (mimic.yaml
+                                                                    # default; replaced by what the strategy produces)
         self._graph = None
         self._static = None
         # Every step (eager warm-up, capture, replay) runs on this one non-default stream: autograd binds each
@@ -112,13 +114,23 @@ class MimicTrainer:
             self.flat.grad_and_scalars.zero_()
         loss_dict = self.sm.forward_inputs(inputs, query_inputs, fold_scale=1.0 / self.accum)
         (loss_dict["loss"] / self.accum).backward()
-        for i, key in enumerate(("loss", "ce_loss", "ffn_mse_loss")):
-            if key in loss_dict:
-                self.flat.scalars[i] += loss_dict[key].detach().float() / self.accum
+        self._accumulate_scalars(loss_dict)
         self.micro += 1
         if self.micro % self.accum == 0:
             self.optimizer_step()
         return loss_dict
+
+    def _accumulate_scalars(self, loss_dict) -> None:
+        """Loss terms of the micro-batch into the tail of the all-reduce buffer.  "loss" first, then the per-term keys the
+        strategy produces (ce_loss, {attn,ffn}_{mse_loss,cos_sim}, logits_kl_loss): fixed by the strategy, hence the same
+        slots on every rank."""
+        keys = ["loss"] + sorted(k for k in loss_dict if k != "loss")
+        if keys != self._scalar_keys:
+            if len(keys) > self.flat.scalars.numel():
+                raise RuntimeError(f"{len(keys)} loss terms, {self.flat.scalars.numel()} scalar slots")
+            self._scalar_keys = keys
+        for i, key in enumerate(keys):
+            self.flat.scalars[i] += loss_dict[key].detach().float() / self.accum
 
     def _advance_schedule(self) -> None:
         """Host side of an optimizer step: step counter, cosine-with-warm-up lr, Adam bias corrections ->
@@ -172,9 +184,7 @@ class MimicTrainer:
             ins, qs = self._static[0][a], self._static[1][a]
             loss_dict = self.sm.forward_inputs(ins if ins else None, qs, fold_scale=1.0 / self.accum)
             (loss_dict["loss"] / self.accum).backward()
-            for i, key in enumerate(("loss", "ce_loss", "ffn_mse_loss")):
-                if key in loss_dict:
-                    self.flat.scalars[i] += loss_dict[key].detach().float() / self.accum
+            self._accumulate_scalars(loss_dict)
         self._device_optimizer_step()
 
     def graph_step(self, batches) -> None:
@@ -198,7 +208,7 @@ class MimicTrainer:
         """Mean over ranks of the loss terms of the last optimizer step (one D2H read)."""
         with self._on_stream():
             vals = (self.flat.scalars / self.world).tolist()
-        return dict(zip(("loss", "ce_loss", "ffn_mse_loss"), vals))
+        return dict(zip(self._scalar_keys, vals))
 
     # encoder.pth, same keys as the reference's save_pretrained (src/utils.py:96-102)
     def state_dict_for_checkpoint(self):

@@ -207,6 +207,22 @@ def test_norm_shift_shapes_and_properties(N, D, stride):
     assert rel(ds, wds) < 1e-3 and rel(dc, wdc) < 1e-3
 
 
+def test_norm_shift_unaligned_parameter_view():
+    """The shift row may live at any 4-byte offset of the trainer's flat parameter buffer (e.g. behind a 30-element
+    scale vector); the result must not depend on it."""
+    from mimic_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    flat = torch.randn(3 + 64, generator=gen).cuda()
+    h = torch.randn(7, 64, generator=gen).cuda()
+    a = ops.norm_shift(h, flat[3:], None)
+    b = ops.norm_shift(h, flat[3:].clone(), None)
+    assert flat[3:].data_ptr() % 16 != 0 and torch.equal(a, b)
+    hl, sl = h.clone().requires_grad_(True), flat.clone().requires_grad_(True)
+    g1 = torch.autograd.grad(ops.norm_shift(hl, sl[3:], None), [hl, sl], torch.ones_like(h))
+    want = NS.norm_shift_bwd(h.cpu(), flat[3:].cpu(), 1.0, torch.ones(7, 64))
+    assert rel(g1[0], want[0]) < 1e-5 and rel(g1[1][3:], want[1]) < 1e-5 and float(g1[1][:3].abs().max()) == 0.0
+
+
 def test_norm_shift_errors_and_empty():
     from mimic_b200 import ops
     shift = torch.zeros(16, device="cuda")
