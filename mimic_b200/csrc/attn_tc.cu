@@ -448,11 +448,13 @@ bool supports(const AttnParams& p, bool backward) {
 int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query tiles per CTA
 int fwd64(const AttnParams& p, cudaStream_t st);  // attn_tc_fwd64.cu: 64-key tiles, two CTAs per SM
 int fwd64p(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64p.cu: the same pipeline in persistent CTAs (static work lists)
+int fwd64w(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64w.cu: eight softmax warps per CTA (opt-in, not yet validated on a GPU)
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
-  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3" / "4": single-tile / ping-pong / 64-key two-CTA (auto persistent) / persistent forced
+  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3" / "4" / "5": single-tile / ping-pong / 64-key two-CTA (auto persistent) / persistent forced / wide softmax
   const int kern = force ? atoi(force) : 3;             // measured on B200: 3 is the fastest at every T
+  if (kern == 5 && (size_t)((p.S + 63) / 64) * 8 < 8000) return fwd64w(p, st);   // experimental, never picked by default
   if ((kern == 3 || kern == 4) && (size_t)((p.S + 63) / 64) * 8 < 16000) {
     // persistent variant: inactive handle (context pass), several tiles per CTA slot, AND the K/V of every (kv head,
     // batch) stream fit L2 together — its CTAs in flight touch all streams at once.  Measured: +8 % (+16 % with a padding
