@@ -1,6 +1,8 @@
-// Forward, 64-key tiles, two CTAs per SM, EIGHT softmax warps per CTA ("wide softmax").  OPT-IN (MIMIC_FWD_KERNEL=5):
-// written at the end of round 1 from the steady-state timeline of attn_tc_fwd64.cu and NOT YET VALIDATED ON A
-// GPU — the default path does not reach this file.
+// Forward, 64-key tiles, two CTAs per SM, EIGHT softmax warps per CTA ("wide softmax").  OPT-IN (MIMIC_FWD_KERNEL=5), an
+// experiment kept for the record: it is correct (60 randomised shapes against the SIMT kernels, scripts/fuzz_attention.py) and
+// 8-16 % SLOWER than the four-warp kernels (scripts/ab_fwd_wide.py: context pass 703 vs 839 TFLOP/s, T=4096 802 vs 899
+// inactive / 802 vs 875 active) — halving every serial phase of the softmax thread does not shorten the step, so that chain is
+// not what bounds the forward.  The default path does not reach this file.
 //
 // Why: in attn_tc_fwd64.cu one thread owns a whole 64-column score row, and the step of the key loop is the serial chain
 // of that thread (TMEM load ~400 cycles, row maximum ~290, exp2 / pack / store ~750, fences ~150) — ~2000 cycles per
