@@ -306,3 +306,17 @@ def test_flat_params_scale_lr_groups():
     with pytest.raises(ValueError):
         AttnFFNShift(make_fake_lmm(64, 3, 4), "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.MULTI_HEAD", None)
     assert AttnFFNShift(make_fake_lmm(64, 3, 4), None, None).register_shift_hooks() == {}
+
+
+def test_every_c_symbol_is_documented_in_integration_md():
+    """include/mimic_b200.h is the drop-in boundary: each entry point must appear in INTEGRATION.md's table of what it
+    replaces in the reference, and in the ctypes binding table (mimic_b200/_lib.py)."""
+    import re
+    from mimic_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "mimic_b200.h")).read()
+    names = set(re.findall(r"MIMIC_API\s+[\w\s\*]+?\b(mimic_\w+)\s*\(", header))
+    assert len(names) >= 20
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert not [n for n in sorted(names) if n not in doc]
+    assert names == set(_lib.EXPORTS)
