@@ -8,6 +8,8 @@
 //   smem: Q 32 KB | K ring 2 x 16 KB | V ring 2 x 16 KB | barriers, w, shift, key bits.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "attn_common.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
@@ -486,7 +488,10 @@ int fwd64(const AttnParams& p, cudaStream_t st) {
   if ((rc = make_map(&to, p.out, p.B, p.H, p.T, p.o_sb, p.o_sh, p.o_st, BM))) return rc;
   if ((rc = make_map(&tk, p.k, p.B, p.Hkv, p.S, p.k_sb, p.k_sh, p.k_ss, BN))) return rc;
   if ((rc = make_map(&tv, p.v, p.B, p.Hkv, p.S, p.v_sb, p.v_sh, p.v_ss, BN))) return rc;
-  const size_t smem = smem_bytes(p.S);
+  size_t smem = smem_bytes(p.S);
+  // diagnosis only: MIMIC_FWD_ONE_CTA pads the request so that a single CTA fits an SM — how much of the two-CTA rate one CTA
+  // alone reaches tells how well the pair overlaps (the convoy question)
+  if (getenv("MIMIC_FWD_ONE_CTA") && smem + (120u << 10) <= (227u << 10)) smem += 120u << 10;
   static size_t configured = 0;
   if (smem > configured) {
     MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

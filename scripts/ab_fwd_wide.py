@@ -1,4 +1,5 @@
-"""A/B in one process: default forward kernels vs the experimental wide-softmax kernel (MIMIC_FWD_KERNEL=5)."""
+"""A/B in one process: default forward kernels vs the experimental wide-softmax kernel (MIMIC_FWD_KERNEL=5) vs the
+one-tile-per-CTA kernel held to one CTA per SM (MIMIC_FWD_ONE_CTA, diagnosis of how well two co-resident CTAs overlap)."""
 import os
 import sys
 import torch
@@ -13,10 +14,14 @@ def run(B, H, Hkv, T, active, reps=10):
     sh, w, b = (torch.randn(H, d, device="cuda"), torch.randn(H, d, device="cuda") * 0.1, torch.randn(H, device="cuda")) if active else (None,) * 3
     fn = lambda: ops.shifted_attention_forward(q, k, v, None, sh, w, b, causal=True, active=active, scale=d ** -0.5)
     out = {}
-    for name, env in (("default", None), ("wide", "5")):
-        if env is None:
-            os.environ.pop("MIMIC_FWD_KERNEL", None)
-        else:
+    for name, env in (("default", None), ("wide", "5"), ("one_cta_per_sm", "one")):
+        os.environ.pop("MIMIC_FWD_KERNEL", None)
+        os.environ.pop("MIMIC_FWD_ONE_CTA", None)
+        os.environ.pop("MIMIC_NO_PERSISTENT", None)
+        if env == "one":                      # the one-tile-per-CTA kernel with occupancy forced to 1 (diagnosis)
+            os.environ["MIMIC_FWD_ONE_CTA"] = "1"
+            os.environ["MIMIC_NO_PERSISTENT"] = "1"
+        elif env is not None:
             os.environ["MIMIC_FWD_KERNEL"] = env
         for _ in range(2):
             fn()
