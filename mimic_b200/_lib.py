@@ -85,9 +85,16 @@ def _load() -> C.CDLL:
                 fcntl.flock(lock, fcntl.LOCK_EX)
                 if not _build.up_to_date():
                     _build.build(force=True)             # needs nvcc
-    except RuntimeError:
+    except RuntimeError as e:
         if not os.path.exists(LIB_PATH):
             raise                     # no library and no way to build it: fail loudly, there is no fallback path
+        # A library exists but it was NOT built from the sources in the tree and could not be rebuilt: kernels and
+        # checked-in code may disagree.  Refuse, unless the caller explicitly accepts the stale binary.
+        if not os.environ.get("MIMIC_ALLOW_STALE_LIB"):
+            raise ImportError(f"libmimic_b200.so is stale (sources changed since it was built) and the rebuild failed: {e}\n"
+                              "fix the build, or set MIMIC_ALLOW_STALE_LIB=1 to bind the old binary anyway") from e
+        import warnings
+        warnings.warn(f"binding a STALE libmimic_b200.so (MIMIC_ALLOW_STALE_LIB set); rebuild failed: {e}", RuntimeWarning)
     lib = _bind(LIB_PATH)             # AttributeError when a prebuilt library is older than the header
     if lib.mimic_abi_version() != 1:
         raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 1; rebuild (python -m mimic_b200.build --force)")

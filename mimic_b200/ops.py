@@ -179,8 +179,9 @@ class _ShiftedAttention(torch.autograd.Function):
     def forward(ctx, q, k, v, shift, w, bias, key_mask, causal, active, scale, impl, sink):
         out, lse_c, lse_full, mu, saved = shifted_attention_forward(
             q, k, v, key_mask, shift, w, bias, causal=causal, active=active, scale=scale, impl=impl)
-        ctx.saved = saved
-        ctx.stats = (out, lse_c, lse_full, mu)
+        # inputs AND the op's own outputs go through save_for_backward: no grad_fn <-> output reference cycle (the
+        # activations are freed by reference counting), and saved-tensor hooks / in-place version checks see them
+        ctx.save_for_backward(*saved, out, lse_c, lse_full, mu)
         ctx.cfg = (causal, active, scale, impl)
         ctx.sink = sink
         ctx.param_dtypes = tuple(None if t is None else t.dtype for t in (shift, w, bias))
@@ -190,10 +191,10 @@ class _ShiftedAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, _d_lse):
         causal, active, scale, impl = ctx.cfg
-        out, lse_c, lse_full, mu = ctx.stats
+        *saved, out, lse_c, lse_full, mu = ctx.saved_tensors
         sink = ctx.sink
         dq, dk, dv, dshift, dw, dbias = shifted_attention_backward(
-            ctx.saved, out, d_out, lse_c, lse_full, mu, causal=causal, active=active, scale=scale, impl=impl,
+            tuple(saved), out, d_out, lse_c, lse_full, mu, causal=causal, active=active, scale=scale, impl=impl,
             dshift=None if sink is None else sink.dshift, dw=None if sink is None else sink.dw,
             dbias=None if sink is None else sink.dbias)
         if sink is not None or not active:
@@ -215,19 +216,18 @@ class _AttentionWithFullLse(torch.autograd.Function):
         zero_h = torch.zeros(H, dtype=torch.float32, device=q.device)
         out, lse_c, lse_full, mu, saved = shifted_attention_forward(
             q, k, v, key_mask, zero_hd, zero_hd, zero_h, causal=causal, active=True, scale=scale, impl=impl)
-        ctx.saved = saved
-        ctx.stats = (out, lse_c, lse_full, mu)
+        ctx.save_for_backward(*saved, out, lse_c, lse_full, mu)
         ctx.cfg = (causal, scale, impl)
         return out, lse_full
 
     @staticmethod
     def backward(ctx, d_out, d_lse_full):
         causal, scale, impl = ctx.cfg
-        out, lse_c, lse_full, mu = ctx.stats
+        *saved, out, lse_c, lse_full, mu = ctx.saved_tensors
         if d_out is None:
             d_out = torch.zeros_like(out)
         dq, dk, dv, _, _, _ = shifted_attention_backward(
-            ctx.saved, out, d_out, lse_c, lse_full, mu, causal=causal, active=True, scale=scale, impl=impl,
+            tuple(saved), out, d_out, lse_c, lse_full, mu, causal=causal, active=True, scale=scale, impl=impl,
             d_lse_full=d_lse_full)
         return dq, dk, dv, None, None, None, None
 
@@ -436,12 +436,18 @@ def _align_forward(ctx, kind, hp, row_to_compact, row_w, grad_scale, assume_fold
     return loss[0]
 
 
+def _unfold(g: torch.Tensor, grad_scale: float) -> torch.Tensor:
+    """Factor that turns a gradient pre-scaled by `grad_scale` into one scaled by the upstream gradient `g`
+    (a zero weight wrote zeros: keep them)."""
+    return g / grad_scale if grad_scale != 0.0 else torch.zeros_like(g)
+
+
 def _align_backward(ctx, g):
     dh = ctx.dh
     if dh is None:
         return (None,) * (5 + len(ctx.shapes))
     if not ctx.assume_folded:
-        dh = dh * (g / ctx.grad_scale).to(dh.dtype)
+        dh = dh * _unfold(g, ctx.grad_scale).to(dh.dtype)
     return (None, None, None, None, None) + tuple(dh[l].view(s) for l, s in enumerate(ctx.shapes))
 
 
@@ -500,7 +506,7 @@ class _KLLoss(torch.autograd.Function):
         if d is None:
             return (None,) * 6
         if not ctx.assume_folded:
-            d = d * (g / ctx.grad_scale).to(d.dtype)
+            d = d * _unfold(g, ctx.grad_scale).to(d.dtype)
         return d.view(ctx.shape), None, None, None, None, None
 
 
@@ -549,7 +555,7 @@ class _CELoss(torch.autograd.Function):
         if d is None:
             return None, None, None, None, None
         if not ctx.assume_folded:
-            d = d * (g / ctx.grad_scale).to(d.dtype)
+            d = d * _unfold(g, ctx.grad_scale).to(d.dtype)
         return d.view(ctx.shape), None, None, None, None
 
 

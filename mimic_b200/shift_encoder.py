@@ -226,6 +226,19 @@ def _apply_rope(q, k, cos, sin):
     return q * cos + _rotate_half(q) * sin, k * cos + _rotate_half(k) * sin
 
 
+def _rotary_takes_position_ids(rotary) -> bool:
+    """Which of the two pre-4.48 rotary-module call conventions `rotary` speaks (cached on the module)."""
+    flag = getattr(rotary, "_mimic_takes_position_ids", None)
+    if flag is None:
+        params = inspect.signature(rotary.forward).parameters
+        flag = "position_ids" in params and "seq_len" not in params
+        try:
+            rotary._mimic_takes_position_ids = flag
+        except AttributeError:
+            pass
+    return flag
+
+
 def key_mask_from_4d(attention_mask: Optional[torch.Tensor], T: int, S: int):
     """HF hands the attention module a 4-D mask [B,1,T,S] (bool: True = attend; float: 0 = attend) or
     None.  The fused op wants (causal flag, [B,S] key mask).  The last query row sees every valid key."""
@@ -262,11 +275,18 @@ def _fused_attn_forward(self, hidden_states, position_embeddings=None, attention
     cos = sin = None
     if position_embeddings is not None:
         cos, sin = position_embeddings
-    elif hasattr(self, "rotary_emb"):                  # pre-4.48 module layout (Idefics v1)
+    elif hasattr(self, "rotary_emb"):                  # pre-4.48 module layout: the attention module owns the rotary table
         kv_len = T + (cache.get_seq_length(self.layer_idx) if cache is not None else 0)
-        cos, sin = self.rotary_emb(v, seq_len=max(kv_len, T))
         pos = position_ids if position_ids is not None else torch.arange(kv_len - T, kv_len, device=q.device)[None]
-        cos, sin = cos[pos], sin[pos]
+        if _rotary_takes_position_ids(self.rotary_emb):
+            # transformers 4.45 MistralRotaryEmbedding / LlamaRotaryEmbedding: forward(x, position_ids) -> gathered
+            # [B,T,d] tables (the call at src/shift_encoder.py:417: self.rotary_emb(value_states, position_ids))
+            cos, sin = self.rotary_emb(v, pos)
+        else:
+            # IdeficsEmbedding (Idefics v1): forward(x, seq_len=) -> [seq_len, d] tables, gathered by position
+            # (src/shift_encoder.py:307-312)
+            cos, sin = self.rotary_emb(v, seq_len=max(kv_len, T))
+            cos, sin = cos[pos], sin[pos]
     if cos is not None:
         if cos.shape[-1] == d:
             q, k = ops.rope_qk(q, k, cos, sin)         # one launch for q and k (HF: ~10 elementwise kernels)

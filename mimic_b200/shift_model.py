@@ -198,11 +198,19 @@ class ShiftModel(nn.Module):
             self._hp_buffers[name] = buf
         return buf
 
-    def forward_inputs(self, inputs: Optional[dict], query_inputs: dict, fold_scale: float = 1.0):
+    def forward_inputs(self, inputs: Optional[dict], query_inputs: dict, fold_scale: float = 1.0,
+                       assume_folded: bool = False):
         """Token-level MimIC step (src/shift_model.py:200-285).  `inputs` = full-context batch
         ([bos] ICE [PAD] query [PAD] answer [eos]), `query_inputs` = query-only batch; both dicts of
         model kwargs containing "input_ids" (attention masks are rebuilt from the pad id like lines
-        212/222).  `fold_scale` multiplies every loss gradient (1/accumulate_grad_batches)."""
+        212/222).
+
+        Gradient contract: the loss kernels write dH / dlogits in the same launch as the loss value, pre-scaled by
+        `weight * fold_scale`.  By default (`assume_folded=False`) the autograd backward rescales them by the gradient
+        that actually arrives at each loss term, so `loss_dict["loss"]` behaves like any differentiable scalar (loss
+        scaling, GradScaler, extra terms all work).  `assume_folded=True` is a promise that the caller backpropagates
+        exactly `fold_scale * loss_dict["loss"]` (MimicTrainer: fold_scale = 1/accumulate_grad_batches) and skips that
+        rescale; any other use of it gives wrong gradients."""
         enc, tok = self.shift_encoder, self._tok
         want_kl = Strategy.LOGITS_KL_DIV in self.strategy
         cos = Strategy.LAYER_WISE_COS_SIM in self.strategy
@@ -253,7 +261,7 @@ class ShiftModel(nn.Module):
             labels = torch.full_like(q_ids, -100)
             labels[:, :-1] = torch.where(query_inputs["attention_mask"][:, 1:], q_ids[:, 1:],
                                          torch.full_like(q_ids[:, 1:], -100))
-            ce = ops.ce_loss(logits, labels, grad_scale=w * fold_scale, assume_folded=True)
+            ce = ops.ce_loss(logits, labels, grad_scale=w * fold_scale, assume_folded=assume_folded)
             loss_dict["ce_loss"] = ce.detach()
             loss_dict["loss"] = loss_dict["loss"] + w * ce
 
@@ -272,7 +280,7 @@ class ShiftModel(nn.Module):
             for n in record_names:
                 hs = list(getattr(enc, n))
                 align = (ops.align_cos if cos else ops.align_mse)(hs, self._hp_buffers[n], row_to_compact, row_w,
-                                                                  grad_scale=aw * fold_scale, assume_folded=True)
+                                                                  grad_scale=aw * fold_scale, assume_folded=assume_folded)
                 layer_loss[n.replace("hidden_states", self.strategy.layer_wise_strategy())] = align
             for k_, v_ in layer_loss.items():
                 loss_dict[k_] = v_.detach()
@@ -281,7 +289,7 @@ class ShiftModel(nn.Module):
         if want_kl:                                                               # step 4, lines 272-283
             aw = float(self.cfg.align_loss_weight)
             kl = ops.kl_loss(logits, prefix_logits, _paired_rows(self.generate_label_mask(query_inputs, 1), prefix_label_mask),
-                             grad_scale=aw * fold_scale, assume_folded=True)
+                             grad_scale=aw * fold_scale, assume_folded=assume_folded)
             loss_dict["logits_kl_loss"] = kl.detach()
             loss_dict["loss"] = loss_dict["loss"] + aw * kl
 

@@ -78,7 +78,7 @@ def cosine_with_warmup(step: int, warmup: int, total: int) -> float:
 class MimicTrainer:
     def __init__(self, shift_model: ShiftModel, *, lr: float = 5e-3, weight_decay: float = 1e-3, warmup_step=0.1,
                  total_steps: int = 1000, grad_clip_val: float = 1.0, accumulate_grad_batches: int = 1,
-                 process_group=None, scale_lr: Optional[float] = None):
+                 process_group=None, scale_lr: Optional[float] = None, distributed: bool = True):
         self.sm = shift_model
         self.sm.check_separators = False            # no host sync inside the step
         self.flat = FlatShiftParams(shift_model.shift_encoder, weight_decay, lr=lr, scale_lr=scale_lr)
@@ -87,8 +87,14 @@ class MimicTrainer:
         self.clip = grad_clip_val
         self.accum = accumulate_grad_batches
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # distributed=False: a single-process trainer inside an initialised job (e.g. a reference step on one rank)
+        self.world = (dist.get_world_size(process_group)
+                      if (distributed and dist.is_available() and dist.is_initialized()) else 1)
         dev = self.flat.param.device
+        if self.world > 1:
+            # Lightning DDP broadcasts rank 0's module state when it wraps the model (config/train.yaml:14): ranks that
+            # were seeded differently, or loaded different checkpoints, must start from identical parameters
+            self.broadcast_state()
         self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)       # lr, bias corrections (device: graph replay)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.opt_step = 0
@@ -101,6 +107,12 @@ class MimicTrainer:
         # leaf's gradient accumulator to the stream of its first use, and a capture only accepts same-stream edges.
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
+    def broadcast_state(self, src: int = 0) -> None:
+        """Rank `src`'s parameters and AdamW moments to every rank (call again after loading a checkpoint on one rank)."""
+        if self.world > 1:
+            for t in (self.flat.param, self.flat.exp_avg, self.flat.exp_avg_sq):
+                dist.broadcast(t, src=src, group=self.pg)
+
     def _on_stream(self):
         return torch.cuda.stream(self.stream) if self.stream is not None else nullcontext()
 
@@ -112,7 +124,7 @@ class MimicTrainer:
         """One micro-batch: forward (2 passes) + backward.  Steps the optimizer every `accum` calls."""
         if self.micro % self.accum == 0:
             self.flat.grad_and_scalars.zero_()
-        loss_dict = self.sm.forward_inputs(inputs, query_inputs, fold_scale=1.0 / self.accum)
+        loss_dict = self.sm.forward_inputs(inputs, query_inputs, fold_scale=1.0 / self.accum, assume_folded=True)
         (loss_dict["loss"] / self.accum).backward()
         self._accumulate_scalars(loss_dict)
         self.micro += 1
@@ -182,7 +194,7 @@ class MimicTrainer:
         self.flat.grad_and_scalars.zero_()
         for a in range(self.accum):
             ins, qs = self._static[0][a], self._static[1][a]
-            loss_dict = self.sm.forward_inputs(ins if ins else None, qs, fold_scale=1.0 / self.accum)
+            loss_dict = self.sm.forward_inputs(ins if ins else None, qs, fold_scale=1.0 / self.accum, assume_folded=True)
             (loss_dict["loss"] / self.accum).backward()
             self._accumulate_scalars(loss_dict)
         self._device_optimizer_step()

@@ -28,11 +28,13 @@ def _adamw_torch(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper, *, betas
     param.sub_(lr / bc1 * exp_avg / (exp_avg_sq.sqrt() / bc2s + eps))
 
 
-def _make_trainer():
+def _make_trainer(seed=0):
+    """NOTE: replaces ops.adamw_step with the torch restatement for the calling process — callers in the pytest
+    process go through the `torch_adamw` fixture, which restores the CUDA front-end afterwards."""
     from tests.test_host_logic import _tiny_lmm
     from mimic_b200 import AttnApproximator, ShiftModel, Strategy, ops
     from mimic_b200.trainer import MimicTrainer
-    torch.manual_seed(0)
+    torch.manual_seed(seed)
     lmm = _tiny_lmm()
     lmm.processor = types.SimpleNamespace(tokenizer=types.SimpleNamespace(pad_token_id=0, bos_token_id=1, padding_side="left"))
     enc = AttnApproximator(lmm, *MIMIC)
@@ -49,7 +51,7 @@ def _rank_grad(rank, n):
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    tr = _make_trainer()
+    tr = _make_trainer(seed=rank)          # ranks initialise DIFFERENTLY: the trainer must broadcast rank 0's state
     assert tr.world == world
     n = tr.flat.numel
     tr.flat.grad.copy_(_rank_grad(rank, n))
@@ -59,7 +61,15 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_mean_gradient_step():
+@pytest.fixture
+def torch_adamw():
+    from mimic_b200 import ops
+    saved = ops.adamw_step
+    yield
+    ops.adamw_step = saved
+
+
+def test_two_rank_step_equals_mean_gradient_step(torch_adamw):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
@@ -69,8 +79,8 @@ def test_two_rank_step_equals_mean_gradient_step():
     p1, s1 = out[1]
     assert torch.equal(p0, p1), "ranks diverged"
     assert s0 == s1 and abs(s0["loss"] - 1.5) < 1e-6 and abs(s0["ffn_mse_loss"] - 3.5) < 1e-6
-    # single process, mean of the two rank gradients
-    tr = _make_trainer()
+    # single process (rank 0's initial parameters: what the broadcast hands every rank), mean of the two rank gradients
+    tr = _make_trainer(seed=0)
     n = tr.flat.numel
     tr.flat.grad.copy_((_rank_grad(0, n) + _rank_grad(1, n)) / 2)
     tr.optimizer_step()

@@ -60,7 +60,7 @@ def test_attention_matches_reference_golden(path, dtype):
     wg = OA.shifted_attention_bwd(q, k, v, shift, g["w"], g["b"], d_out, **kw)
     assert rel(out, want) < tol, "out"
     for name, got in grads.items():
-        assert rel(got, wg[name]) < tol * (2.0 if dtype == torch.bfloat16 else 1.0), name
+        assert rel(got, wg[name]) < tol, name
     if dtype == torch.float32:
         rv = g["row_valid"].bool()[:, :, None, None].expand_as(g["out"])
         assert rel(out.cpu()[rv], g["out"][rv]) < tol
@@ -111,7 +111,7 @@ def test_attention_matches_oracle(case, dtype):
     tol = TOL[dtype]
     assert rel(out, want) < tol, "out"
     for name, got in grads.items():
-        assert rel(got, wg[name]) < tol * (2.0 if dtype == torch.bfloat16 else 1.0), name
+        assert rel(got, wg[name]) < tol, name
 
 
 def test_inactive_is_plain_causal_attention_bitwise():

@@ -63,7 +63,7 @@ def _step(preset, dtype, oracle_attention, lora=False, strategies=None, **cfg_ov
     return model, enc, {k: float(v) for k, v in loss.items()}, grads
 
 
-@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 4e-2)], ids=["fp32-d64", "bf16-d128"])
+@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 1e-2)], ids=["fp32-d64", "bf16-d128"])
 def test_idefics_v1_layout_cross_attention_untouched(dtype, heads, tol):
     from mimic_b200.backbone import CrossAttention
     kw = dict(num_layers=5, hidden_size=256, intermediate_size=512, num_attention_heads=heads, num_key_value_heads=heads,
@@ -76,11 +76,13 @@ def test_idefics_v1_layout_cross_attention_untouched(dtype, heads, tol):
     assert len(enc.attn_shift_handles) == 5 and enc.attn_shift.shape[0] == 5
     for k in ("loss", "ce_loss", "ffn_mse_loss"):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
+    errs = {n: rel(grads[n], grads_o[n]) for n in grads}
+    print("whole-step gradient rel-L2 (max):", max(errs.values()))
     for n in grads:
-        assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
+        assert errs[n] < (tol * 2 if dtype == torch.bfloat16 else tol), n
 
 
-@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 4e-2)], ids=["fp32-d64", "bf16-d128"])
+@pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 1e-2)], ids=["fp32-d64", "bf16-d128"])
 def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
     kw = dict(num_layers=3, hidden_size=256, intermediate_size=512, num_attention_heads=heads, num_key_value_heads=heads,
               vocab_size=1000)
@@ -90,8 +92,10 @@ def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
     assert sum(1 for n in grads if ".lora_" in n) == 6
     for k in ("loss", "ce_loss", "ffn_mse_loss"):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
+    errs = {n: rel(grads[n], grads_o[n]) for n in grads}
+    print("whole-step gradient rel-L2 (max):", max(errs.values()))
     for n in grads:
-        assert rel(grads[n], grads_o[n]) < (tol * 5 if dtype == torch.bfloat16 else tol), n
+        assert errs[n] < (tol * 2 if dtype == torch.bfloat16 else tol), n
 
 
 def test_attn_record_point_config():
@@ -150,3 +154,37 @@ def test_decode_with_kv_cache_matches_oracle():
         logits[which] = outs
     for a, b in zip(logits["cuda"], logits["oracle"]):
         assert a.shape == b.shape and rel(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("style", ["position_ids", "seq_len"])
+def test_rotary_module_conventions_of_pinned_transformers(style):
+    """transformers 4.45.2 hands the replaced forward NO position_embeddings: the attention module owns `rotary_emb`.
+    Idefics2 / Mistral: rotary_emb(x, position_ids) -> [B,T,d] (src/shift_encoder.py:417); Idefics v1:
+    rotary_emb(x, seq_len=) -> [seq_len,d] tables gathered by position (307-312).  Both must give what the
+    position_embeddings path gives."""
+    from mimic_b200 import AttnApproximator, HookedModel
+    from mimic_b200.backbone import build_synthetic, rope_cos_sin, synthetic_processor
+    from mimic_b200.shift_encoder import _fused_attn_forward
+    kw = dict(num_layers=1, hidden_size=256, intermediate_size=512, num_attention_heads=2, num_key_value_heads=2, vocab_size=64)
+    model, name = build_synthetic("idefics2-8b", dtype=torch.bfloat16, device="cuda", **kw)
+    enc = AttnApproximator(HookedModel(model, name, processor=synthetic_processor()), *MIMIC).cuda()
+    attn = model.model.text_model.layers[0].self_attn
+    theta, d = model.config.rope_theta, model.config.head_dim
+
+    class MistralStyle(torch.nn.Module):
+        def forward(self, x, position_ids):
+            return rope_cos_sin(position_ids, d, theta, x.dtype)
+
+    class IdeficsStyle(torch.nn.Module):
+        def forward(self, x, seq_len=None):
+            cos, sin = rope_cos_sin(torch.arange(seq_len, device=x.device)[None], d, theta, x.dtype)
+            return cos[0], sin[0]
+
+    B, T = 2, 40
+    x = torch.randn(B, T, 256, device="cuda").bfloat16()
+    pos = torch.arange(T, device="cuda")[None].expand(B, T)
+    call = lambda **k: _fused_attn_forward(attn, x, module_name="model.text_model.layers.0.self_attn", shift_encoder=enc, **k)[0]
+    want = call(position_embeddings=rope_cos_sin(pos, d, theta, x.dtype))
+    attn.rotary_emb = MistralStyle() if style == "position_ids" else IdeficsStyle()
+    assert torch.equal(call(position_ids=pos), want)
+    assert torch.equal(call(), want)                      # position_ids omitted: 0..T-1

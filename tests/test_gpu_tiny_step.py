@@ -163,3 +163,29 @@ def test_tiny_step_licv_matches_reference():
     assert ops.launch_count - n0 >= 4 + 4 + 2                 # 4 hook launches each way, CE and KL
     for (n, p), g in zip(params.items(), grads):
         assert rel(g, z["grad." + n]) < 2e-4, n
+
+
+def test_tiny_step_trainer_update_matches_reference_adamw():
+    """f1 end to end: ONE MimicTrainer step (flat gradient buffer written by the kernels -> global-norm clip -> on-device
+    AdamW with the reference's two weight-decay groups) lands on the parameters the REFERENCE step produced with
+    clip_grad_norm_(1.0) + torch.optim.AdamW(lr 5e-3, wd 1e-3 / 0 on bias) — keys `after.*` of tiny_step.npz
+    (src/shift_model.py:306-372, train.yaml grad_clip_val)."""
+    from mimic_b200 import Strategy
+    from mimic_b200.trainer import MimicTrainer
+    z = np.load(os.path.join(GOLDEN, "tiny_step.npz"))
+    enc, sm = _tiny_setup(z, Strategy.LM_LOSS | Strategy.LAYER_WISE_MSE)
+    # constant lr 5e-3 at the first step: no warm-up, cosine(0) = 1
+    tr = MimicTrainer(sm, lr=5e-3, weight_decay=1e-3, warmup_step=0, total_steps=10 ** 9, grad_clip_val=1.0)
+    full_ids, qa_ids = torch.from_numpy(z["full_ids"]).cuda(), torch.from_numpy(z["qa_ids"]).cuda()
+    ld = tr.micro_step({"input_ids": full_ids}, {"input_ids": qa_ids})
+    assert tr.opt_step == 1
+    assert abs(float(ld["loss"]) - float(z["loss"])) < 2e-5 * float(z["loss"])
+    params = {n: p for n, p in enc.named_parameters() if p.requires_grad and not n.startswith("lmm")}
+    for n, p in params.items():
+        moved = float(np.abs(z["after." + n] - z["init." + n]).max())
+        assert moved > 0, n                                          # the fixture's step really moved this parameter
+        # compare the UPDATE (after - init): the parameters themselves are dominated by their initial values
+        upd, want = p.detach().cpu().double() - torch.from_numpy(z["init." + n]).double(), \
+            torch.from_numpy(z["after." + n]).double() - torch.from_numpy(z["init." + n]).double()
+        assert float((upd - want).norm() / want.norm()) < 2e-3, n
+        assert float((p.detach().cpu() - torch.from_numpy(z["after." + n])).abs().max()) < 2e-6, n

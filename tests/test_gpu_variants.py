@@ -203,7 +203,7 @@ def test_norm_shift_shapes_and_properties(N, D, stride):
     sl, cl = shift.clone().requires_grad_(True), scale.clone().requires_grad_(True)
     dh, ds, dc = torch.autograd.grad(ops.norm_shift(hl, sl, cl), [hl, sl, cl], dy)
     wdh, wds, wdc = NS.norm_shift_bwd(h.double().cpu(), shift.double().cpu(), 0.6, dy.double().cpu())
-    assert rel(dh[rows.cuda()], wdh[rows]) < 2e-2
+    assert rel(dh[rows.cuda()], wdh[rows]) < 1e-2
     assert rel(ds, wds) < 1e-3 and rel(dc, wdc) < 1e-3
 
 
