@@ -78,7 +78,8 @@ def rope_qk(q, k, cos, sin):
 
 
 def record_gather(src, src_row, dst):
-    dst.copy_(src.reshape(-1, src.shape[-1]).index_select(0, src_row.long()))
+    ok = src_row >= 0                                   # the row plan is padded with -1 up to its capacity
+    dst.copy_(src.reshape(-1, src.shape[-1]).index_select(0, src_row.clamp_min(0).long()) * ok[:, None])
 
 
 def align_mse(hs, hp, row_to_compact, row_w, grad_scale=1.0, assume_folded=False):

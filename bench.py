@@ -231,8 +231,8 @@ def main():
     # the real stdout for the JSON line and point fd 1 at stderr, so the NCCL log stays visible (stderr) and countable.
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"             # communicator / rank lines (on stderr, see above)
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
 
     import torch

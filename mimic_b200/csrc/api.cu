@@ -37,6 +37,19 @@ int num_sms() {
   return n;
 }
 
+// L2 working-set budget for kernels that choose their work order by what stays cache-resident: a third of the device's
+// L2 (both dies keep their own copy of lines that SMs of both dies read), queried once.
+long long l2_budget_bytes() {
+  static long long b = 0;
+  if (b == 0) {
+    int dev = 0, l2 = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) != cudaSuccess || l2 <= 0)
+      l2 = 126 << 20;
+    b = (long long)l2 / 3;
+  }
+  return b;
+}
+
 }  // namespace mimic
 
 extern "C" {

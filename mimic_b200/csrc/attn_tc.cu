@@ -450,25 +450,41 @@ int fwd64(const AttnParams& p, cudaStream_t st);  // attn_tc_fwd64.cu: 64-key ti
 int fwd64p(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64p.cu: the same pipeline in persistent CTAs (static work lists)
 int fwd64w(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64w.cu: eight softmax warps per CTA (opt-in, not yet validated on a GPU)
 
+int fwdp(const AttnParams& p, cudaStream_t st);   // attn_tc_fwdp.cu: persistent, two 128-row query tiles ping-ponged over 128-key tiles
+bool fwdp_supports(const AttnParams& p);
+
+// Forward kernel choice.  MIMIC_FWD_KERNEL (read ONCE per process; A/B scripts set it before the first call) forces a family:
+// "1" single-tile / "2" ping-pong, one item per CTA / "3" 64-key tiles, two CTAs per SM (persistent when it pays) /
+// "4" that one persistent always / "5" wide softmax (experiment) / "6" persistent ping-pong.  Default: 6 where it applies
+// (more than one query tile), else 3.
+static int forced_fwd_kernel() {
+  static const int k = [] {
+    const char* e = getenv("MIMIC_FWD_KERNEL");
+    return e ? atoi(e) : 0;
+  }();
+  return k;
+}
+static bool env_flag(const char* name) { return getenv(name) != nullptr; }
+
 int fwd(const AttnParams& p, cudaStream_t st) {
-  // more than one query tile: the ping-pong kernel; a single tile (query pass of a VQA step, decode): this file
-  const char* force = getenv("MIMIC_FWD_KERNEL");       // "1" / "2" / "3" / "4" / "5": single-tile / ping-pong / 64-key two-CTA (auto persistent) / persistent forced / wide softmax
-  const int kern = force ? atoi(force) : 3;             // measured on B200: 3 is the fastest at every T
+  static const bool no_persistent = env_flag("MIMIC_NO_PERSISTENT");
+  const int forced = forced_fwd_kernel();
+  if ((forced == 0 || forced == 6) && fwdp_supports(p)) return fwdp(p, st);
+  const int kern = (forced == 0 || forced == 6) ? 3 : forced;
   if (kern == 5 && (size_t)((p.S + 63) / 64) * 8 < 8000) return fwd64w(p, st);   // experimental, never picked by default
   if ((kern == 3 || kern == 4) && (size_t)((p.S + 63) / 64) * 8 < 16000) {
     // persistent variant: inactive handle (context pass), several tiles per CTA slot, AND the K/V of every (kv head,
-    // batch) stream fit L2 together — its CTAs in flight touch all streams at once.  Measured: +8 % (+16 % with a padding
-    // mask) at the Idefics2 context pass; -2 % with the shift active (equal work per tile, per-item tables); -17 % at
-    // T = 8192 with 64 MHA streams (268 MB of K/V)
+    // batch) stream fit the L2 budget together — its CTAs in flight touch all streams at once
     const long long items = (long long)((p.T + 127) / 128) * p.H * p.B;
     const long long kv_bytes = 2LL * p.B * p.Hkv * p.S * p.d * 2;
-    const bool persistent = kern == 4 || (!p.active && items >= 4LL * 2 * 148 && kv_bytes <= (48LL << 20));
-    if (persistent && !getenv("MIMIC_NO_PERSISTENT")) return fwd64p(p, st);
+    const bool persistent = kern == 4 || (!p.active && items >= 4LL * 2 * num_sms() && kv_bytes <= l2_budget_bytes());
+    if (persistent && !no_persistent) return fwd64p(p, st);
     return fwd64(p, st);
   }
   if (kern == 2 && p.T > BM) return fwd2(p, st);
   AttnParams pd = p;
-  if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pd.debug_flags = atoi(e);
+  static const int dbg_flags = [] { const char* e = getenv("MIMIC_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
+  pd.debug_flags = dbg_flags;
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_map(&tq, p.q, p.B, p.H, p.T, p.q_sb, p.q_sh, p.q_st, 128))) return rc;

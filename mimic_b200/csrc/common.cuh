@@ -139,5 +139,6 @@ __device__ __forceinline__ float fast_ex2(float x) {
 }
 
 int num_sms();
+long long l2_budget_bytes();
 
 }  // namespace mimic

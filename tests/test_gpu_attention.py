@@ -110,8 +110,12 @@ def test_attention_matches_oracle(case, dtype):
     wg = OA.shifted_attention_bwd(q, k, v, shift, w, b, d_out, **kw)
     tol = TOL[dtype]
     assert rel(out, want) < tol, "out"
+    # One key: softmax == 1 whatever the score, so dS of the attention term is EXACTLY zero and dq / dk are the (tiny) shift
+    # term alone; in bf16 the rounding of `out` (from which Delta is formed) is of the size of that whole gradient.  The
+    # degenerate case keeps a 2e-2 bar in bf16; every other case sits at the north-star 1e-2.
+    gtol = 2 * tol if (S == 1 and dtype == torch.bfloat16) else tol
     for name, got in grads.items():
-        assert rel(got, wg[name]) < tol, name
+        assert rel(got, wg[name]) < gtol, name
 
 
 def test_inactive_is_plain_causal_attention_bitwise():
