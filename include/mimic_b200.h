@@ -146,6 +146,32 @@ MIMIC_API int mimic_record_gather(const void* src, int64_t src_row_stride, int32
                         int32_t N, int32_t D, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row plan: the integer side of one MimIC pass in ONE launch, from the token ids [B, S] (int64):
+ *   attn_mask  [B,S] u8   ids != pad_id                                   (src/shift_model.py:212, 222)
+ *   label_mask [B,S] u8   ShiftModel.generate_label_mask(inputs, num_separator, keep_bos) (75-110): tokens after
+ *                         the num_separator-th PAD that is not leading padding (left_padding != 0: pads before the first
+ *                         non-pad token are padding, not separators), minus pads
+ *   selection  select_mode 0: the label mask; 1: non-pad and != bos_id (the query rows of the alignment loss, 253-257)
+ *   rows [cap] i32        flat index b*S+s of the k-th selected token, ascending (the order masked_select / boolean
+ *                         indexing enumerate, 131-141), -1 behind the last one
+ *   row_to_compact [B*S]  k for a selected token, else -1
+ *   row_w [cap] f32       w_scale / max(N_b, 1) for the compact rows of sample b (N_b = its selected tokens), 0 behind
+ *   lm_labels [B,S] i64   ids[b,s+1] where that token is not a pad, else -100: the shifted labels of the in-model LM
+ *                         loss of transformers 4.45 (call site 238-250)
+ *   paired [B*S] i32      pair_src[k] for the k-th selected token (k < pair_cap), else -1: pairs it with the k-th
+ *                         row of another plan (boolean-mask indexing on both sides, 185-186)
+ *   count [1], row_counts [B], sep_counts [B] i32: selected tokens in all / per sample; separators per sample
+ *                         (sep_counts[b] < num_separator is the reference's ValueError, 97-100: host-side check)
+ * Every output pointer may be NULL.  Replaces the comparisons / cumsums / nonzero / .item() loop of the reference
+ * and their ~40 eager launches per step.
+ * ------------------------------------------------------------------------------------------ */
+MIMIC_API int mimic_row_plan(const int64_t* ids, int32_t B, int32_t S, int64_t pad_id, int64_t bos_id,
+                   int32_t left_padding, int32_t num_separator, int32_t select_mode, int32_t keep_bos, float w_scale,
+                   uint8_t* attn_mask, uint8_t* label_mask, int32_t* rows, int32_t cap, int32_t* row_to_compact,
+                   float* row_w, int64_t* lm_labels, const int32_t* pair_src, int32_t pair_cap, int32_t* paired,
+                   int32_t* count, int32_t* row_counts, int32_t* sep_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layer-wise alignment loss, Strategy.LAYER_WISE_MSE, forward + backward in one pass.
  * Replaces ShiftModel.calculate_layer_wise_loss (src/shift_model.py:145-179) and its autograd:
  *   loss = mean_i mean_{l,t,d} (H_i - H'_i)^2 = sum_{l,n,d} row_w[n] * (H[l][row[n]] - H'[l][n])^2

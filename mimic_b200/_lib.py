@@ -44,6 +44,9 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mimic_record_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "mimic_row_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mimic_mse_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "mimic_mse_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,

@@ -13,12 +13,18 @@
 //   warps 4-7   softmax of query tile 1      (192 registers)             S1 [128,256)  O1 [384,512)
 //   warps 8-11  epilogue: O_x / l, + mu*shift, bf16, TMA store (72)      P_x = first 64 columns of S_x (bf16 pairs)
 //   warp 12     MMA issuer (one elected lane issues)
-//   warp 13     TMA producer: ONE thread multiplexes the K, V and Q streams by polling their "empty" barriers, so a
-//               stream that has to wait (V behind a PV, Q behind the item's last QK^T) never holds up another
+//   warp 13 K producer | warp 14 V producer (one thread each, sleeping on the barrier it needs)
+//   warp 15     item scheduler (global ticket counter -> shared-memory ring) + Q producer, one polling thread
 //   smem: Q0 Q1 | K ring x2 | V ring x2 (32 KB tiles, 128B swizzle) | 16 KB output staging | barriers, stats, key bits
 // MMA issue order (tcgen05 ops of one thread execute in order; P_x aliases S_x, so QK_x(j+1) follows PV_x(j)):
 //   QK0(0) QK1(0) | per key tile j:  [P0(j)] PV0(j) QK0(j+1)   [P1(j)] PV1(j) QK1(j+1)
+// P_x(j) is handed over in FOUR 32-key quarters (one barrier per quarter — a waiter must never fall two phases behind): the PV MMAs of the first quarters
+// run while the softmax warps still exponentiate the later ones, which takes ~3/4 of PV_x(j) off the chain
+// softmax_x(j) -> PV_x(j) -> QK_x(j+1) -> softmax_x(j+1) that bounds a tile's step.
 #include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
 
 #include "attn_common.cuh"
 #include "tc_host.cuh"
@@ -38,13 +44,14 @@ constexpr int THREADS = 512;          // warps 14, 15 only take part in the regi
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.f;
 constexpr int OFF_Q = 0, OFF_K = 2 * TILE, OFF_V = 4 * TILE, OFF_OST = 6 * TILE, OFF_BAR = OFF_OST + HALF;
-constexpr int N_BARS = 26;
-constexpr int OFF_TMEM = OFF_BAR + 32 * 8, OFF_STATS = OFF_TMEM + 16, OFF_KBITS = OFF_STATS + 2 * 128 * 8;
+constexpr int NSCHED = 3;                        // depth of the item ring between the scheduler thread and the consumer roles
+constexpr int OFF_TMEM = OFF_BAR + 48 * 8, OFF_SCHED = OFF_TMEM + 16, OFF_STATS = OFF_SCHED + 16, OFF_KBITS = OFF_STATS + 2 * 128 * 8;
 constexpr int KBITS_MAX = 16384;
 constexpr int SMEM_MAX = OFF_KBITS + KBITS_MAX;
 static_assert(SMEM_MAX <= 227 * 1024, "shared memory budget");
 enum { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 6, V_FULL = 8, V_EMPTY = 10, S_FULL = 12, SOFT_DONE = 14,
-       PV_DONE = 16, O_FULL = 18, O_EMPTY = 20, ST_FULL = 22, ST_EMPTY = 24 };
+       PV_DONE = 16, O_FULL = 18, O_EMPTY = 20, ST_FULL = 22, ST_EMPTY = 24, SCHED_FULL = 26, SCHED_EMPTY = 30, P_PART = 34 };
+constexpr int SCHED_CONSUMERS = 8 + 4 + 1 + 3;   // softmax warps, epilogue warps, MMA warp, the K / V / Q producer threads
 constexpr uint32_t IDESC_QK = idesc_bf16(BM, BN, 0, 0);
 constexpr uint32_t IDESC_PV = idesc_bf16(BM, HD, 0, 1);
 // 512 threads launch with 128 registers each (ptxas sizes a kernel that uses setmaxnreg by whole warpgroups); the epilogue
@@ -76,6 +83,9 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 
 __device__ __forceinline__ uint32_t low_bitsp(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
+constexpr int N_TICKETS = 256;
+__device__ unsigned int g_fwdp_tickets[2 * N_TICKETS];   // zero-initialised; every launch leaves its pair at zero again
+
 struct FwdItem {
   int h, b, kvh;
   int t0[2], jd[2], n[2];
@@ -88,7 +98,7 @@ struct FwdCounts {       // what the MMA issuer needs of an item
 __global__ void __launch_bounds__(fp::THREADS, 1)
 attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, AttnParams p,
-                    int sec_hb) {
+                    int sec_hb, unsigned int* ticket, int static_sched) {
   using namespace fp;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -98,6 +108,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* sO = smem + OFF_OST;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  volatile int* sched = reinterpret_cast<volatile int*>(smem + OFF_SCHED);   // item ring written by the scheduler thread
   float2* stats = reinterpret_cast<float2*>(smem + OFF_STATS);          // [2][128] (1 / l_c, mu)
   uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_KBITS);  // [B][words] when a key mask is given
 
@@ -113,7 +124,9 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   // item -> (query-tile pair, head, batch).  Order: sections of `sec_hb` (head, batch) streams whose K/V fit L2
   // together; inside a section the pair rank is slowest (descending work under the causal mask) and the head fastest
-  // (a GQA group shares its K/V through L2).  CTA c takes items c, c + grid, c + 2 grid, ...
+  // (a GQA group shares its K/V through L2).  Items are handed out DYNAMICALLY: the producer thread draws the CTA's next
+  // item from a global ticket counter and publishes it in a small shared-memory ring that every role reads in order
+  // (a static round-robin left SMs idle for 14 % of the kernel at T = 4096: the lists do not sum to equal work).
   auto decode = [&](int it) {
     FwdItem m;
     const int per_sec = n_qp * sec_hb;
@@ -148,6 +161,17 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     return m;
   };
 
+  // k-th item of this CTA (every lane of the calling warp waits and reads), >= n_items when the work has run out
+  auto sched_get = [&](uint32_t k) -> int {
+    mbar_wait_q(&bars[SCHED_FULL + (k % NSCHED)], (k / NSCHED) & 1);
+    return sched[k % NSCHED];
+  };
+  // the calling warp is done with its k-th item (one arrival per consumer warp)
+  auto sched_release = [&](uint32_t k) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[SCHED_EMPTY + (k % NSCHED)]);
+  };
+
   // ------------------------------------------------ prologue (once per CTA) ------------------------------------------------
   if (warp == 13) {
     if (lane == 0) {
@@ -165,6 +189,11 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_init(&bars[O_EMPTY + i], 128);
         mbar_init(&bars[ST_FULL + i], 128);
         mbar_init(&bars[ST_EMPTY + i], 128);
+        for (int q = 0; q < 4; ++q) mbar_init(&bars[P_PART + 4 * i + q], 128);
+      }
+      for (int i = 0; i < NSCHED; ++i) {
+        mbar_init(&bars[SCHED_FULL + i], 1);
+        mbar_init(&bars[SCHED_EMPTY + i], SCHED_CONSUMERS);
       }
       fence_barrier_init();
       prefetch_tmap(&tm_q);
@@ -199,84 +228,93 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 14) {
-    reg_dec<REG_MISC>();                                   // idle warps of the last warpgroup: hand their registers over
-  } else if (warp == 13) {
-    // ===================== TMA producer: K, V and Q streams multiplexed by one thread =====================
+  if (warp == 13 || warp == 14) {
+    // ===================== K producer (warp 13) / V producer (warp 14): one thread each, blocking waits =====================
+    // (a 2-stage ring makes the issue time of the next load part of the critical path: each stream sleeps on exactly the
+    // barrier it needs — a thread multiplexing the streams by polling added ~15 % to the kernel)
     reg_dec<REG_MISC>();
     if (lane == 0) {
-      // each stream walks the CTA's items with its own cursor; a stream issues its next load when the "empty" barrier of
-      // the slot it needs has completed (non-blocking probe), otherwise the thread moves on to the next stream
-      int itK = blockIdx.x, jK = 0, itV = blockIdx.x, jV = 0, itQ = blockIdx.x, xQ = 0;
-      uint32_t gK = 0, gV = 0, qc0 = 0, qc1 = 0;
-      FwdItem mK = decode(min(itK, n_items - 1)), mV = mK, mQ = mK;
+      const bool is_k = warp == 13;
+      uint8_t* ring = is_k ? sK : sV;
+      const CUtensorMap* tm = is_k ? &tm_k : &tm_v;
+      const int FULL = is_k ? K_FULL : V_FULL, EMPTY = is_k ? K_EMPTY : V_EMPTY;
+      uint32_t g = 0;
+      for (uint32_t k = 0;; ++k) {
+        const int it = sched_get(k);
+        if (it >= n_items) break;
+        const FwdItem m = decode(it);
+        const int n_loads = is_k ? m.nmax : m.nv;
+        for (int j = 0; j < n_loads; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait_q(&bars[EMPTY + st], ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(&bars[FULL + st], TILE);
+          tma_load_4d(ring + st * TILE, tm, &bars[FULL + st], 0, j * BN, m.kvh, m.b);
+          tma_load_4d(ring + st * TILE + HALF, tm, &bars[FULL + st], 64, j * BN, m.kvh, m.b);
+        }
+        mbar_arrive(&bars[SCHED_EMPTY + (k % NSCHED)]);
+      }
+    }
+  } else if (warp == 15) {
+    // ===================== scheduler + Q producer: one thread, polling (neither is latency-critical) =====================
+    reg_dec<REG_MISC>();
+    if (lane == 0) {
+      uint32_t pub = 0, kQ = 0, qc0 = 0, qc1 = 0;          // items published (the last one is the end sentinel); Q-stream ordinal
+      bool pub_done = false, hQ = false, eQ = false;
+      int xQ = 0;
+      FwdItem mQ = decode(0);
       uint32_t idle = 0;
-      while (itK < n_items || itV < n_items || itQ < n_items) {
+      while (!eQ) {
         bool progressed = false;
-        if (itK < n_items) {
-          if (jK >= mK.nmax) {
-            itK += gridDim.x;
-            jK = 0;
-            if (itK < n_items) mK = decode(itK);
+        if (!pub_done) {
+          const int slot = pub % NSCHED;
+          if (pub < (uint32_t)NSCHED || mbar_test_wait(&bars[SCHED_EMPTY + slot], ((pub / NSCHED) & 1) ^ 1)) {
+            const int it = static_sched ? (int)(blockIdx.x + pub * gridDim.x) : (int)atomicAdd(ticket, 1u);
+            sched[slot] = it;
+            mbar_arrive(&bars[SCHED_FULL + slot]);           // release: the store above is visible to the waiters
+            ++pub;
+            if (it >= n_items) pub_done = true;
             progressed = true;
-          } else {
-            const int st = gK & 1;
-            if (mbar_test_wait(&bars[K_EMPTY + st], ((gK >> 1) & 1) ^ 1)) {
-              mbar_expect_tx(&bars[K_FULL + st], TILE);
-              tma_load_4d(sK + st * TILE, &tm_k, &bars[K_FULL + st], 0, jK * BN, mK.kvh, mK.b);
-              tma_load_4d(sK + st * TILE + HALF, &tm_k, &bars[K_FULL + st], 64, jK * BN, mK.kvh, mK.b);
-              ++gK;
-              ++jK;
-              progressed = true;
-            }
           }
         }
-        if (itV < n_items) {
-          if (jV >= mV.nv) {
-            itV += gridDim.x;
-            jV = 0;
-            if (itV < n_items) mV = decode(itV);
+        if (!hQ) {
+          if (kQ < pub) {
+            const int it = sched[kQ % NSCHED];
+            if (it >= n_items) eQ = true; else { mQ = decode(it); hQ = true; xQ = 0; }
             progressed = true;
-          } else {
-            const int st = gV & 1;
-            if (mbar_test_wait(&bars[V_EMPTY + st], ((gV >> 1) & 1) ^ 1)) {
-              mbar_expect_tx(&bars[V_FULL + st], TILE);
-              tma_load_4d(sV + st * TILE, &tm_v, &bars[V_FULL + st], 0, jV * BN, mV.kvh, mV.b);
-              tma_load_4d(sV + st * TILE + HALF, &tm_v, &bars[V_FULL + st], 64, jV * BN, mV.kvh, mV.b);
-              ++gV;
-              ++jV;
-              progressed = true;
-            }
           }
-        }
-        if (itQ < n_items) {
-          if (xQ >= 2) {
-            itQ += gridDim.x;
-            xQ = 0;
-            if (itQ < n_items) mQ = decode(itQ);
+        } else if (xQ >= 2) {
+          mbar_arrive(&bars[SCHED_EMPTY + (kQ % NSCHED)]);
+          hQ = false;
+          ++kQ;
+          progressed = true;
+        } else if ((xQ ? mQ.n[1] : mQ.n[0]) == 0) {
+          ++xQ;                                              // tile without any key tile to visit: no Q needed
+          progressed = true;
+        } else {
+          const uint32_t qc = xQ ? qc1 : qc0;
+          if (mbar_test_wait(&bars[Q_EMPTY + xQ], (qc & 1) ^ 1)) {
+            mbar_expect_tx(&bars[Q_FULL + xQ], TILE);
+            const int tq0 = xQ ? mQ.t0[1] : mQ.t0[0];
+            tma_load_4d(sQ + xQ * TILE, &tm_q, &bars[Q_FULL + xQ], 0, tq0, mQ.h, mQ.b);        // rows >= T arrive as zeros
+            tma_load_4d(sQ + xQ * TILE + HALF, &tm_q, &bars[Q_FULL + xQ], 64, tq0, mQ.h, mQ.b);
+            if (xQ) ++qc1; else ++qc0;
+            ++xQ;
             progressed = true;
-          } else if ((xQ ? mQ.n[1] : mQ.n[0]) == 0) {
-            ++xQ;                                              // tile without any key tile to visit: no Q needed
-            progressed = true;
-          } else {
-            const uint32_t qc = xQ ? qc1 : qc0;
-            if (mbar_test_wait(&bars[Q_EMPTY + xQ], (qc & 1) ^ 1)) {
-              mbar_expect_tx(&bars[Q_FULL + xQ], TILE);
-              const int tq0 = xQ ? mQ.t0[1] : mQ.t0[0];
-              tma_load_4d(sQ + xQ * TILE, &tm_q, &bars[Q_FULL + xQ], 0, tq0, mQ.h, mQ.b);        // rows >= T arrive as zeros
-              tma_load_4d(sQ + xQ * TILE + HALF, &tm_q, &bars[Q_FULL + xQ], 64, tq0, mQ.h, mQ.b);
-              if (xQ) ++qc1; else ++qc0;
-              ++xQ;
-              progressed = true;
-            }
           }
         }
         if (progressed) {
           idle = 0;
         } else {
-          __nanosleep(64);
+          __nanosleep(32);
           if (++idle > (1u << 24)) __trap();                   // a protocol bug must not hang the GPU box
         }
+      }
+      // the last CTA to run out of work re-arms the ticket counter for the next launch that uses it
+      __threadfence();
+      if (!static_sched && atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
+        ticket[0] = 0u;
+        ticket[1] = 0u;
+        __threadfence();
       }
     }
   } else if (warp == 12) {
@@ -285,7 +323,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     constexpr uint32_t HI = desc_hi_sw128(1024);
     const uint32_t q_lo0 = desc_lo(smem_u32(sQ), 16), k_lo0 = desc_lo(smem_u32(sK), 16);
     const uint32_t v_lo0 = desc_lo(smem_u32(sV), HALF);                 // V as MN-major B: d halves 16 KB apart
-    uint32_t sc0 = 0, sc1 = 0, qc0 = 0, qc1 = 0, oc0 = 0, oc1 = 0;
+    uint32_t sc0 = 0, sc1 = 0, qc0 = 0, qc1 = 0, oc0 = 0, oc1 = 0, pp0 = 0, pp1 = 0;
     uint32_t kb = 0, vb = 0;                                            // ring index of the item's first K / V tile
     bool pre0 = false, pre1 = false;
     auto counts = [&](int it) {
@@ -319,49 +357,65 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       __syncwarp();
     };
-    FwdCounts m = counts(blockIdx.x < n_items ? blockIdx.x : 0);
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const bool has_next = it + (int)gridDim.x < n_items;
+    int it = sched_get(0);
+    FwdCounts m = counts(it < n_items ? it : 0);
+    for (uint32_t k = 0; it < n_items; ++k) {
+      // the next item is only needed from the round in which the first tile finishes (its QK^T'(0) goes out behind the
+      // tile's last PV): fetch it there, so the scheduler has the whole item to publish it
+      int it_next = n_items;
+      bool has_next = false, have_nx = false;
       FwdCounts nx = m;
-      if (has_next) nx = counts(it + gridDim.x);
       if (m.n[0] > 0 && !pre0) issue_qk(0, m.n[0], m.n[1], 0, kb);
       if (m.n[1] > 0 && !pre1) issue_qk(1, m.n[1], m.n[1], 0, kb);
       pre0 = pre1 = false;
       for (int j = 0; j < m.nmax; ++j) {
+        if (!have_nx && j >= m.nmax - 2) {
+          it_next = sched_get(k + 1);
+          has_next = it_next < n_items;
+          if (has_next) nx = counts(it_next);
+          have_nx = true;
+        }
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           if (j >= m.n[x]) continue;
-          mbar_wait_q(&bars[SOFT_DONE + x], (x ? sc1 : sc0) & 1);
-          if (x) ++sc1; else ++sc0;
-          tc_fence_after();
+          const uint32_t g = vb + j;
+          const int vs = g & 1;
           if (j <= m.jd[x]) {
-            if (j == 0) mbar_wait_q(&bars[O_EMPTY + x], ((x ? oc1 : oc0) & 1) ^ 1);   // the previous item's O_x has been drained
-            const uint32_t g = vb + j;
-            const int vs = g & 1;
+            // what PV_x(j) needs besides P — the V tile and, for the first PV of an item, a drained O_x — is confirmed BEFORE
+            // the softmax hand-over, so that nothing but the issue itself follows it (neither depends on this softmax step)
+            if (j == 0) mbar_wait_q(&bars[O_EMPTY + x], ((x ? oc1 : oc0) & 1) ^ 1);
             mbar_wait_q(&bars[V_FULL + vs], (g >> 1) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              // A: P_x in TMEM (128 keys = 64 packed columns, 8 per K step); B: V_j [128 keys][d], 16 keys = 2 KB per step
-              const uint32_t v_lo = v_lo0 + vs * (TILE >> 4);
-              const uint32_t a_p = tmem_base + x * BN, d_o = tmem_base + 256 + x * BN;
-              if (j > 0) {
+          }
+          if (j <= m.jd[x]) {
+            // A: P_x in TMEM (128 keys = 64 packed columns, 8 per K step); B: V_j [128 keys][d], 16 keys = 2 KB per step.
+            // Quarter q of P_x (keys 32 q .. 32 q + 31) arrives with phase q of the step on P_PART; the last one also means
+            // "S_x is consumed" (there is no separate SOFT_DONE arrival on a step that has a PV).
+            const uint32_t v_lo = v_lo0 + vs * (TILE >> 4);
+            const uint32_t a_p = tmem_base + x * BN, d_o = tmem_base + 256 + x * BN;
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k) mma_ts_c<true>(d_o, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
-              } else {
+            for (int q = 0; q < 4; ++q) {
+              mbar_wait_q(&bars[P_PART + 4 * x + q], (x ? pp1 : pp0) & 1);
+              tc_fence_after();
+              if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k) {
-                  if (k == 0) mma_ts_c<false>(d_o, a_p, desc64(HI, v_lo), IDESC_PV);
-                  else mma_ts_c<true>(d_o, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV);
+                for (int k = 2 * q; k < 2 * q + 2; ++k)
+                  mma_ts(d_o, a_p + k * 8, desc64(HI, v_lo + k * (2048 >> 4)), IDESC_PV, (j > 0 || k > 0) ? 1u : 0u);
+                if (q == 3) {
+                  if (x == 1 || j > m.jd[1]) tc_commit(&bars[V_EMPTY + vs]);
+                  tc_commit(&bars[PV_DONE + x]);
+                  if (j == m.jd[x]) tc_commit(&bars[O_FULL + x]);
                 }
               }
-              if (x == 1 || j > m.jd[1]) tc_commit(&bars[V_EMPTY + vs]);
-              tc_commit(&bars[PV_DONE + x]);
-              if (j == m.jd[x]) tc_commit(&bars[O_FULL + x]);
+              __syncwarp();
             }
-            __syncwarp();
+            if (x) ++pp1; else ++pp0;
             if (j == m.jd[x]) {
               if (x) ++oc1; else ++oc0;
             }
+          } else {
+            mbar_wait_q(&bars[SOFT_DONE + x], (x ? sc1 : sc0) & 1);          // a step without PV: S_x has been consumed
+            if (x) ++sc1; else ++sc0;
+            tc_fence_after();
           }
           if (j + 1 < m.n[x]) {
             issue_qk(x, m.n[x], m.n[1], j + 1, kb);
@@ -371,9 +425,15 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
       }
+      if (!have_nx) {                                        // item without any key tile
+        it_next = sched_get(k + 1);
+        if (it_next < n_items) nx = counts(it_next);
+      }
       kb += m.nmax;
       vb += m.nv;
       m = nx;
+      it = it_next;
+      sched_release(k);
     }
   } else if (warp >= 8) {
     // ===================== epilogue warpgroup: O_x / l_c + mu * shift -> bf16 -> staging -> TMA store =====================
@@ -383,7 +443,9 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool issuer = threadIdx.x == 256;
     uint32_t oc[2] = {0, 0}, stc[2] = {0, 0};
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (uint32_t k = 0;; ++k) {
+      const int it = sched_get(k);
+      if (it >= n_items) break;
       const FwdItem m = decode(it);
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
@@ -444,6 +506,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         if (has_pv) ++oc[x];
       }
+      sched_release(k);
     }
     if (issuer) bulk_wait0();
   } else {
@@ -458,10 +521,15 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint8_t* sQx = sQ + x * TILE;
     uint32_t sc = 0, pvc = 0, qc = 0, stc = 0;
 
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (uint32_t k = 0;; ++k) {
+      const int it = sched_get(k);
+      if (it >= n_items) break;
       const FwdItem m = decode(it);
       const int t0 = x ? m.t0[1] : m.t0[0];               // (no runtime-indexed arrays: they would live in local memory)
-      if (t0 >= T) continue;                              // tile outside the tensor: nothing to load, compute or store
+      if (t0 >= T) {                                      // tile outside the tensor: nothing to load, compute or store
+        sched_release(k);
+        continue;
+      }
       const int nloc = x ? m.n[1] : m.n[0], jd = x ? m.jd[1] : m.jd[0], h = m.h, b = m.b;
       const int t = t0 + r;
       const bool row_ok = t < T;
@@ -548,8 +616,13 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               m_c = m_new;
             }
           }
-          l_c += exp_pack_store128(s, scale2, -m_c, t_S);        // packed fp32x2 FMA/ADD, 4 independent sum chains
-          tc_wait_st();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                          // P in four quarters, each handed to the MMA issuer as it lands
+            l_c += exp_pack_store32(*reinterpret_cast<const float(*)[32]>(s + 32 * i), scale2, -m_c, t_S + 16 * i);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars[P_PART + 4 * x + i]);
+          }
         } else if (c_excl) {
           float s[128];
           tmem_ld32(t_S, *reinterpret_cast<float(*)[32]>(s));
@@ -571,6 +644,9 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < 4; ++i) tmem_st16(t_S + 16 * i, z);
             tc_wait_st();
+            tc_fence_before();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbar_arrive(&bars[P_PART + 4 * x + i]);
           }
         } else if (c_zero) {
           if (has_pv) {                                    // another warp of the tile has visible keys: this one contributes P = 0
@@ -580,25 +656,51 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < 4; ++i) tmem_st16(t_S + 16 * i, z);
             tc_wait_st();
+            tc_fence_before();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbar_arrive(&bars[P_PART + 4 * x + i]);
           }
         } else {
-          // ---- MIXED: pass 1 = masked maxima, pass 2 = one exp2 per score against the reference of its class; the score
-          // tile is re-read from TMEM chunk by chunk (runtime loops: a quarter of the code of the unrolled version) ----
+          // ---- MIXED (diagonal / padded / ragged tiles): two passes over 32-column chunks re-read from TMEM, each chunk
+          // classified warp-uniformly so that only chunks that really mix visible, excluded and absent keys pay for mask
+          // words — on a causal diagonal that is ONE chunk of four per warp:
+          //   0 every key visible to every row   1 (active) every key excluded for every row
+          //   2 contributes nothing (hidden + inactive, or past S, or no valid row)   3 partial: masked arithmetic
+          auto chunk_class = [&](int i, uint32_t& kw) -> int {
+            const int c0 = key0 + 32 * i;
+            const bool none_in = c0 >= S, in_all = c0 + 32 <= S;
+            kw = kbits ? kbits[j * 4 + i] : low_bitsp(S - c0);
+            if (rows_all_ok && kw == 0xFFFFFFFFu && (!p.causal || c0 + 31 <= lim_lo)) return 0;
+            const bool hid_all = tw0 >= T || none_in || (p.causal && c0 > lim_hi);
+            if (hid_all) {
+              if (none_in || tw0 >= T || !p.active) return 2;
+              if (in_all && rows_all_ok) return 1;
+            }
+            return 3;
+          };
           float mv = -INFINITY, mx = -INFINITY;
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
+            uint32_t kw;
+            const int cls = chunk_class(i, kw);
+            if (cls == 2) continue;
             float s[32];
             tmem_ld32(t_S + 32 * i, s);
-            const uint32_t inr = low_bitsp(S - key0 - 32 * i);
-            const uint32_t cz = p.causal ? low_bitsp(t + off - key0 - 32 * i + 1) : 0xFFFFFFFFu;
-            const uint32_t kw = kbits ? kbits[j * 4 + i] : inr;
-            const uint32_t vw = row_ok ? (kw & cz) : 0u;
-            const uint32_t xw = (p.active && row_ok) ? (inr & ~vw) : 0u;
             tc_wait_ld();
+            if (cls == 0) {
+              mv = fmaxf(mv, max32(s));
+            } else if (cls == 1) {
+              mx = fmaxf(mx, max32(s));
+            } else {
+              const uint32_t inr = low_bitsp(S - key0 - 32 * i);
+              const uint32_t cz = p.causal ? low_bitsp(t + off - key0 - 32 * i + 1) : 0xFFFFFFFFu;
+              const uint32_t vw = row_ok ? (kw & cz) : 0u;
+              const uint32_t xw = (p.active && row_ok) ? (inr & ~vw) : 0u;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              mv = ((vw >> c) & 1u) ? fmaxf(mv, s[c]) : mv;
-              mx = ((xw >> c) & 1u) ? fmaxf(mx, s[c]) : mx;
+              for (int c = 0; c < 32; ++c) {
+                mv = ((vw >> c) & 1u) ? fmaxf(mv, s[c]) : mv;
+                mx = ((xw >> c) & 1u) ? fmaxf(mx, s[c]) : mx;
+              }
             }
           }
           mv *= scale2;
@@ -638,35 +740,68 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           float rowsum = 0.f, es = 0.f;
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
+            uint32_t kw;
+            const int cls = chunk_class(i, kw);
+            if (cls == 2) {
+              if (has_pv) {                                  // P = 0 for this chunk (another chunk / warp of the tile has a PV)
+                uint32_t z[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) z[c] = 0u;
+                tmem_st16(t_S + 16 * i, z);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bars[P_PART + 4 * x + i]);
+              }
+              continue;
+            }
+            // P chunk i (16 packed columns) lies inside score chunks <= i: always LOAD the scores of chunk i before storing P
             float s[32];
             tmem_ld32(t_S + 32 * i, s);
-            const uint32_t inr = low_bitsp(S - key0 - 32 * i);
-            const uint32_t cz = p.causal ? low_bitsp(t + off - key0 - 32 * i + 1) : 0xFFFFFFFFu;
-            const uint32_t kw = kbits ? kbits[j * 4 + i] : inr;
-            const uint32_t vw = row_ok ? (kw & cz) : 0u;
-            const uint32_t xw = (p.active && row_ok) ? (inr & ~vw) : 0u;
             tc_wait_ld();
-            uint32_t pk[16];
+            if (cls == 1 && has_pv) {
+              uint32_t z[16];
 #pragma unroll
-            for (int c2 = 0; c2 < 16; ++c2) {
-              const bool v0 = (vw >> (2 * c2)) & 1u, v1 = (vw >> (2 * c2 + 1)) & 1u;
-              const bool x0 = (xw >> (2 * c2)) & 1u, x1 = (xw >> (2 * c2 + 1)) & 1u;
-              const float e0 = ex2(fmaf(s[2 * c2], scale2, v0 ? ref_v : ref_x));
-              const float e1 = ex2(fmaf(s[2 * c2 + 1], scale2, v1 ? ref_v : ref_x));
-              const float p0 = v0 ? e0 : 0.f, p1 = v1 ? e1 : 0.f;
-              rowsum += p0 + p1;
-              es += (x0 ? e0 : 0.f) + (x1 ? e1 : 0.f);
-              pk[c2] = pack_bf16(p0, p1);
+              for (int c = 0; c < 16; ++c) z[c] = 0u;
+              tmem_st16(t_S + 16 * i, z);
             }
-            if (has_pv) tmem_st16(t_S + 16 * i, pk);        // P chunk i lies inside score chunks <= i: already consumed
+            if (cls == 0) {
+              if (has_pv) rowsum += exp_pack_store32(s, scale2, ref_v, t_S + 16 * i);
+            } else if (cls == 1) {
+              es += expsum32(s, scale2, ref_x);
+            } else {
+              const uint32_t inr = low_bitsp(S - key0 - 32 * i);
+              const uint32_t cz = p.causal ? low_bitsp(t + off - key0 - 32 * i + 1) : 0xFFFFFFFFu;
+              const uint32_t vw = row_ok ? (kw & cz) : 0u;
+              const uint32_t xw = (p.active && row_ok) ? (inr & ~vw) : 0u;
+              uint32_t pk[16];
+#pragma unroll
+              for (int c2 = 0; c2 < 16; ++c2) {
+                const bool v0 = (vw >> (2 * c2)) & 1u, v1 = (vw >> (2 * c2 + 1)) & 1u;
+                const bool x0 = (xw >> (2 * c2)) & 1u, x1 = (xw >> (2 * c2 + 1)) & 1u;
+                const float e0 = ex2(fmaf(s[2 * c2], scale2, v0 ? ref_v : ref_x));
+                const float e1 = ex2(fmaf(s[2 * c2 + 1], scale2, v1 ? ref_v : ref_x));
+                const float p0 = v0 ? e0 : 0.f, p1 = v1 ? e1 : 0.f;
+                rowsum += p0 + p1;
+                es += (x0 ? e0 : 0.f) + (x1 ? e1 : 0.f);
+                pk[c2] = pack_bf16(p0, p1);
+              }
+              if (has_pv) tmem_st16(t_S + 16 * i, pk);
+            }
+            if (has_pv) {                                    // quarter i of P is in place (stored above whatever its class)
+              tc_wait_st();
+              tc_fence_before();
+              mbar_arrive(&bars[P_PART + 4 * x + i]);
+            }
           }
           l_c += rowsum;
           l_x += es;
-          tc_wait_st();
         }
-        if (has_pv) ++pvc;
-        tc_fence_before();
-        mbar_arrive(&bars[SOFT_DONE + x]);
+        if (has_pv) {
+          ++pvc;                                             // the four P_PART arrivals of the step stand for SOFT_DONE
+        } else {
+          tc_fence_before();
+          mbar_arrive(&bars[SOFT_DONE + x]);
+        }
       }
 
       // ---- item end: row statistics -> epilogue warpgroup (shared memory) and global ----
@@ -691,6 +826,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           p.mu[ridx] = mu;
         }
       }
+      sched_release(k);
     }
   }
   tc_fence_before();
@@ -731,7 +867,14 @@ int fwdp(const AttnParams& p, cudaStream_t st) {
   if (sec > HB) sec = HB;
   const int n_items = ((p.T + 2 * BM - 1) / (2 * BM)) * HB;
   const int grid = n_items < num_sms() ? n_items : num_sms();
-  attn_fwd_tcp_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec);
+  // ticket counters: a ring of self-resetting (next item, CTAs done) pairs in device memory, one pair per launch in
+  // flight — launches on different streams never share a pair; a captured launch keeps replaying its own
+  static std::atomic<unsigned> seq{0};
+  unsigned int* tickets = nullptr;
+  MIMIC_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_fwdp_tickets));
+  unsigned int* ticket = tickets + 2 * (seq.fetch_add(1) % N_TICKETS);
+  static const int static_sched = getenv("MIMIC_FWDP_STATIC") ? 1 : 0;       // A/B only: round-robin instead of tickets
+  attn_fwd_tcp_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec, ticket, static_sched);
   MIMIC_LAUNCH_OK("attn_fwd_tcp_kernel");
   return MIMIC_OK;
 }

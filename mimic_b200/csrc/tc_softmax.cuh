@@ -77,6 +77,25 @@ __device__ __forceinline__ float exp_pack_store64(const float (&s)[64], float sc
   return t.x + t.y;
 }
 
+// P = exp2(s * scale2 + neg_m) for 32 columns -> 16 bf16 pairs -> TMEM columns [t_P, t_P + 16); returns sum(P)
+__device__ __forceinline__ float exp_pack_store32(const float (&s)[32], float scale2, float neg_m, uint32_t t_P) {
+  const float2 sc = make_float2(scale2, scale2), ng = make_float2(neg_m, neg_m);
+  float2 sum[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sum[k] = make_float2(0.f, 0.f);
+  uint32_t pk[16];
+#pragma unroll
+  for (int c2 = 0; c2 < 16; ++c2) {
+    const float2 a = __ffma2_rn(make_float2(s[2 * c2], s[2 * c2 + 1]), sc, ng);
+    const float2 e = make_float2(ptx::ex2(a.x), ptx::ex2(a.y));
+    sum[c2 & 3] = __fadd2_rn(sum[c2 & 3], e);
+    pk[c2] = ptx::pack_bf16(e.x, e.y);
+  }
+  ptx::tmem_st16(t_P, pk);
+  const float2 t = __fadd2_rn(__fadd2_rn(sum[0], sum[1]), __fadd2_rn(sum[2], sum[3]));
+  return t.x + t.y;
+}
+
 // sum of exp2(s * scale2 - m_new) over 32 columns, and their max (for tiles that are entirely "excluded")
 __device__ __forceinline__ float max32(const float (&s)[32]) {
   float m[4];

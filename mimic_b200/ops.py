@@ -379,6 +379,49 @@ def record_gather(src: torch.Tensor, src_row: torch.Tensor, dst: torch.Tensor) -
     _count(1)
 
 
+class RowPlan:
+    """Outputs of kernel P (mimic_row_plan) for one batch of token ids; None where not requested."""
+    __slots__ = ("attn_mask", "label_mask", "rows", "row_to_compact", "row_w", "lm_labels", "paired", "count", "row_counts",
+                 "sep_counts")
+
+
+def row_plan(ids: torch.Tensor, *, pad_id: int, bos_id: int, left_padding: bool, num_separator: int = 0, select: str = "label",
+             keep_bos: bool = False, cap: int = 0, w_scale: float = 0.0, want_attn_mask: bool = True, want_label_mask: bool = False,
+             want_row_to_compact: bool = False, want_row_w: bool = False, want_lm_labels: bool = False,
+             pair_src: Optional[torch.Tensor] = None) -> RowPlan:
+    """ONE launch for the integer side of a MimIC pass (include/mimic_b200.h, mimic_row_plan): attention mask, label mask
+    (ShiftModel.generate_label_mask), compact row plan (ascending flat indices, -1 padded to `cap`), row -> compact index,
+    per-row loss weights, shifted LM labels, pairing with another plan.  ids [B,S] int64 on the device; no host sync."""
+    _require_cuda(ids, pair_src)
+    if ids.dtype != torch.int64 or ids.dim() != 2:
+        raise MimicError(f"row_plan: ids must be int64 [B,S] (got {ids.dtype}, {tuple(ids.shape)})")
+    ids = ids.contiguous()
+    B, S = ids.shape
+    dev = ids.device
+    out = RowPlan()
+    out.attn_mask = torch.empty(B, S, dtype=torch.bool, device=dev) if want_attn_mask else None
+    out.label_mask = torch.empty(B, S, dtype=torch.bool, device=dev) if want_label_mask else None
+    out.rows = torch.empty(cap, dtype=torch.int32, device=dev) if cap > 0 else None
+    out.row_to_compact = torch.empty(B * S, dtype=torch.int32, device=dev) if want_row_to_compact else None
+    out.row_w = torch.empty(cap, dtype=torch.float32, device=dev) if (want_row_w and cap > 0) else None
+    out.lm_labels = torch.empty(B, S, dtype=torch.int64, device=dev) if want_lm_labels else None
+    out.paired = torch.empty(B * S, dtype=torch.int32, device=dev) if pair_src is not None else None
+    counts = torch.empty(1 + 2 * B, dtype=torch.int32, device=dev)
+    out.count, out.row_counts, out.sep_counts = counts[:1], counts[1:1 + B], counts[1 + B:]
+    if pair_src is not None:
+        pair_src = pair_src.to(torch.int32).contiguous()
+    _ev = timer.start("row_plan")
+    check(lib.mimic_row_plan(_ptr(ids), B, S, int(pad_id), int(bos_id), int(bool(left_padding)), int(num_separator),
+                             {"label": 0, "non_pad_non_bos": 1}[select], int(bool(keep_bos)), float(w_scale),
+                             _ptr(out.attn_mask), _ptr(out.label_mask), _ptr(out.rows), int(cap), _ptr(out.row_to_compact),
+                             _ptr(out.row_w), _ptr(out.lm_labels), _ptr(pair_src), 0 if pair_src is None else pair_src.numel(),
+                             _ptr(out.paired), counts.data_ptr(), counts.data_ptr() + 4, counts.data_ptr() + 4 * (1 + B),
+                             _stream()), "mimic_row_plan")
+    timer.stop(_ev)
+    _count(1)
+    return out
+
+
 class _AlignMSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hp, row_to_compact, row_w, grad_scale, assume_folded, *hs):

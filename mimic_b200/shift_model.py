@@ -91,29 +91,22 @@ class ShiftModel(nn.Module):
     def dtype(self):
         return next(self.lmm.model.parameters()).dtype
 
-    # ---- src/shift_model.py:75-110, vectorised on device (no per-sample .item()) ----------------
+    # ---- src/shift_model.py:75-110: kernel P (one launch, no per-sample .item()) ---------------------
     def generate_label_mask(self, inputs, num_separator, keep_bos=False):
         input_ids = inputs["input_ids"]
-        pad_mask = input_ids == self._tok.pad_token_id
-        non_pad = ~pad_mask
-        left = self._tok.padding_side == "left"
-        if left:
-            bos_position = non_pad.long().argmax(dim=1)
-            sep = pad_mask & (torch.arange(input_ids.shape[1], device=input_ids.device)[None] > bos_position[:, None])
-        else:
-            sep = pad_mask
-        n_sep_before = sep.long().cumsum(dim=1) - sep.long()       # separators strictly before position
-        label_mask = (n_sep_before >= num_separator) & non_pad     # strictly after the n-th separator
-        if getattr(self, "check_separators", True):
-            if bool((sep.sum(dim=1) < num_separator).any()):
-                bad = int((sep.sum(dim=1) < num_separator).nonzero()[0])
-                raise ValueError(f"Sequence {bad} has fewer pad tokens ({int(sep[bad].sum())}) "
-                                 f"than num_separator ({num_separator})")
-        if keep_bos:
-            if not left:
-                raise NameError("bos_position is only defined for left padding (reference behaviour)")
-            label_mask[torch.arange(input_ids.shape[0], device=input_ids.device), bos_position] = True
-        return label_mask
+        tok = self._tok
+        left = tok.padding_side == "left"
+        if keep_bos and not left:
+            raise NameError("bos_position is only defined for left padding (reference behaviour)")
+        plan = ops.row_plan(input_ids, pad_id=tok.pad_token_id, bos_id=getattr(tok, "bos_token_id", -1) or -1, left_padding=left,
+                            num_separator=num_separator, select="label", keep_bos=keep_bos, want_attn_mask=False,
+                            want_label_mask=True)
+        if getattr(self, "check_separators", True):                # the reference's ValueError (97-100): one host read
+            sep = plan.sep_counts.tolist()
+            for i, n in enumerate(sep):
+                if n < num_separator:
+                    raise ValueError(f"Sequence {i} has fewer pad tokens ({n}) than num_separator ({num_separator})")
+        return plan.label_mask
 
     def remove_hooks(self, hooks):                       # src/shift_model.py:112-119
         for name, handles in hooks.items():
@@ -214,28 +207,35 @@ class ShiftModel(nn.Module):
         enc, tok = self.shift_encoder, self._tok
         want_kl = Strategy.LOGITS_KL_DIV in self.strategy
         cos = Strategy.LAYER_WISE_COS_SIM in self.strategy
-        prefix_logits = prefix_label_mask = None
+        prefix_logits = prefix_rows_kl = None
         loss_dict = {"loss": 0.0}
         hooks = enc.register_record_hooks()
         q_ids = query_inputs["input_ids"]
         B, T = q_ids.shape
-        query_inputs = dict(query_inputs)
-        query_inputs["attention_mask"] = q_ids != tok.pad_token_id
         layer_wise = self.strategy.has_layer_wise()
         record_names = [n for n in vars(enc) if "hidden_states" in n]
         N_cap = B * T
+        D, L = enc.lmm_hidden_dim, enc.lmm_layers
+        ids_kw = dict(pad_id=tok.pad_token_id, bos_id=tok.bos_token_id, left_padding=tok.padding_side == "left")
+        # kernel P, query pass: attention mask, the query rows of the alignment loss with their compact index and weight
+        # 1 / (B L [D] N_b) (lines 253-257, 145-179), the shifted LM labels — one launch
+        plan_q = ops.row_plan(q_ids, select="non_pad_non_bos", cap=N_cap if layer_wise else 0,
+                              w_scale=1.0 / (B * L * (1 if cos else D)), want_row_to_compact=layer_wise,
+                              want_row_w=layer_wise, want_lm_labels=Strategy.LM_LOSS in self.strategy, **ids_kw)
+        query_inputs = dict(query_inputs)
+        query_inputs["attention_mask"] = plan_q.attn_mask
 
         if self.strategy != Strategy.LM_LOSS:
             inputs = dict(inputs)
-            inputs["attention_mask"] = inputs["input_ids"] != tok.pad_token_id
+            # kernel P, context pass: attention mask + the rows after the first PAD separator (generate_label_mask(inputs, 1))
+            plan_c = ops.row_plan(inputs["input_ids"], num_separator=1, select="label", cap=N_cap, **ids_kw)
+            inputs["attention_mask"] = plan_c.attn_mask
             if layer_wise:
                 if not record_names:
                     raise RuntimeError("Layer wise loss requires to record hidden states, but no any "
                                        "*_hidden_states in shift encoder.")
-                rows_ctx, n_ctx = _selected_rows(self.generate_label_mask(inputs, 1), N_cap)
                 # one [L, N_cap, D] H' buffer; with two record points the hook order is attn then mlp per layer
-                D, L = enc.lmm_hidden_dim, enc.lmm_layers
-                plans = {n: RecordPlan(rows_ctx, self._hp_buffer(n, L, N_cap, D, self.dtype, q_ids.device))
+                plans = {n: RecordPlan(plan_c.rows, self._hp_buffer(n, L, N_cap, D, self.dtype, q_ids.device))
                          for n in record_names}
                 enc.record_plan = plans
             # step 1: full-context forward, no grad, adapters off (line 225-226); hooks gather H' rows
@@ -247,7 +247,9 @@ class ShiftModel(nn.Module):
             enc.record_plan = None
             if want_kl:
                 prefix_logits = out1["logits"] if not isinstance(out1, torch.Tensor) else out1
-                prefix_label_mask = self.generate_label_mask(inputs, 2)        # answer + [EOS] rows (line 235)
+                # answer + [EOS] rows of the context pass (line 235), as a compact row list for the pairing below
+                prefix_rows_kl = ops.row_plan(inputs["input_ids"], num_separator=2, select="label", cap=N_cap,
+                                              want_attn_mask=False, **ids_kw).rows
 
         # step 2: shifted query forward (lines 237-243)
         hooks.update(enc.register_shift_hooks())
@@ -258,28 +260,16 @@ class ShiftModel(nn.Module):
 
         if Strategy.LM_LOSS in self.strategy:
             w = 1.0 if self.strategy == Strategy.LM_LOSS else float(self.cfg.ce_loss_weight)
-            labels = torch.full_like(q_ids, -100)
-            labels[:, :-1] = torch.where(query_inputs["attention_mask"][:, 1:], q_ids[:, 1:],
-                                         torch.full_like(q_ids[:, 1:], -100))
-            ce = ops.ce_loss(logits, labels, grad_scale=w * fold_scale, assume_folded=assume_folded)
+            ce = ops.ce_loss(logits, plan_q.lm_labels, grad_scale=w * fold_scale, assume_folded=assume_folded)
             loss_dict["ce_loss"] = ce.detach()
             loss_dict["loss"] = loss_dict["loss"] + w * ce
 
         if layer_wise:
-            mq = query_inputs["attention_mask"] & (q_ids != tok.bos_token_id)     # lines 253-257
-            flat = mq.reshape(-1)
-            rank = flat.long().cumsum(0) - 1
-            row_to_compact = torch.where(flat, rank, torch.full_like(rank, -1)).to(torch.int32)
-            nq = mq.sum(dim=1).clamp_min(1).float()                               # [B]
-            D, L = enc.lmm_hidden_dim, enc.lmm_layers
-            w_row = (1.0 / (B * L * (1 if cos else D))) / nq                      # weight of a row of sample b
-            rows_q, _ = _selected_rows(mq, N_cap)
-            row_w = w_row[(rows_q.clamp_min(0) // T).long()]
             aw = float(self.cfg.align_loss_weight)
             layer_loss = {}
             for n in record_names:
                 hs = list(getattr(enc, n))
-                align = (ops.align_cos if cos else ops.align_mse)(hs, self._hp_buffers[n], row_to_compact, row_w,
+                align = (ops.align_cos if cos else ops.align_mse)(hs, self._hp_buffers[n], plan_q.row_to_compact, plan_q.row_w,
                                                                   grad_scale=aw * fold_scale, assume_folded=assume_folded)
                 layer_loss[n.replace("hidden_states", self.strategy.layer_wise_strategy())] = align
             for k_, v_ in layer_loss.items():
@@ -288,8 +278,10 @@ class ShiftModel(nn.Module):
 
         if want_kl:                                                               # step 4, lines 272-283
             aw = float(self.cfg.align_loss_weight)
-            kl = ops.kl_loss(logits, prefix_logits, _paired_rows(self.generate_label_mask(query_inputs, 1), prefix_label_mask),
-                             grad_scale=aw * fold_scale, assume_folded=assume_folded)
+            # k-th selected query row (generate_label_mask(query_inputs, 1)) <-> k-th selected context row: kernel P pairs them
+            paired = ops.row_plan(q_ids, num_separator=1, select="label", want_attn_mask=False, pair_src=prefix_rows_kl,
+                                  **ids_kw).paired
+            kl = ops.kl_loss(logits, prefix_logits, paired, grad_scale=aw * fold_scale, assume_folded=assume_folded)
             loss_dict["logits_kl_loss"] = kl.detach()
             loss_dict["loss"] = loss_dict["loss"] + aw * kl
 
