@@ -40,6 +40,9 @@ MIMIC_API const char* mimic_last_attn_impl(void);
 /* Debug: device buffer of n_entries uint64 that CTA (0,0,0) of the tcgen05 backward kernel fills with
  * (tag << 48 | clock) records — a per-role timeline for tuning.  NULL disables (default). */
 MIMIC_API void mimic_debug_set_trace(void* device_u64_buffer, size_t n_entries);
+/* Debug / tests: force the forward kernel family of the tcgen05 path for later calls (0 = automatic choice, -1 = the
+ * MIMIC_FWD_KERNEL environment variable; 3 = 64-key tiles, 6 = persistent ping-pong, see csrc/attn_tc.cu). */
+MIMIC_API void mimic_debug_force_fwd_kernel(int kernel);
 
 /* ------------------------------------------------------------------------------------------
  * Shifted self-attention.

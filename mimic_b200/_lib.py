@@ -32,6 +32,7 @@ EXPORTS = {
     "mimic_last_error": (C.c_char_p, []),
     "mimic_last_attn_impl": (C.c_char_p, []),
     "mimic_debug_set_trace": (None, [C.c_void_p, C.c_size_t]),
+    "mimic_debug_force_fwd_kernel": (None, [C.c_int]),
     "mimic_shifted_attn_fwd": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 12),
     "mimic_shifted_attn_bwd_workspace": (C.c_size_t, [C.POINTER(AttnDesc)]),
     "mimic_shifted_attn_bwd": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 9 + [C.c_int64] * 3 +

@@ -1,7 +1,7 @@
 // Library-wide state: error string, implementation tag, device query.
 #include <cstring>
 
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace mimic {
 
@@ -57,4 +57,5 @@ int mimic_abi_version(void) { return MIMIC_ABI_VERSION; }
 const char* mimic_last_error(void) { return mimic::g_err; }
 const char* mimic_last_attn_impl(void) { return mimic::g_impl; }
 void mimic_debug_set_trace(void* device_u64_buffer, size_t n_entries) { mimic::set_trace(device_u64_buffer, n_entries); }
+void mimic_debug_force_fwd_kernel(int kernel) { mimic::tc::force_fwd_kernel(kernel); }
 }

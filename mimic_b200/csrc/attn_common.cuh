@@ -44,6 +44,7 @@ namespace tc {
 bool supports(const AttnParams& p, bool backward);
 int fwd(const AttnParams& p, cudaStream_t st);
 int bwd(const AttnParams& p, cudaStream_t st);
+void force_fwd_kernel(int k);   // test / A-B hook behind mimic_debug_force_fwd_kernel
 }  // namespace tc
 
 }  // namespace mimic

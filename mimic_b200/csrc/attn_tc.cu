@@ -451,25 +451,27 @@ int fwd64p(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64p.cu: the same
 int fwd64w(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64w.cu: eight softmax warps per CTA (opt-in, not yet validated on a GPU)
 
 int fwdp(const AttnParams& p, cudaStream_t st);   // attn_tc_fwdp.cu: persistent, two 128-row query tiles ping-ponged over 128-key tiles
-bool fwdp_supports(const AttnParams& p);
+bool fwdp_supports(const AttnParams& p, bool forced);
 
 // Forward kernel choice.  MIMIC_FWD_KERNEL (read ONCE per process; A/B scripts set it before the first call) forces a family:
 // "1" single-tile / "2" ping-pong, one item per CTA / "3" 64-key tiles, two CTAs per SM (persistent when it pays) /
 // "4" that one persistent always / "5" wide softmax (experiment) / "6" persistent ping-pong.  Default: 6 where it applies
 // (more than one query tile), else 3.
+static int g_forced_fwd = -1;            // mimic_debug_force_fwd_kernel(); -1 = MIMIC_FWD_KERNEL (read once) or 0
+void force_fwd_kernel(int k) { g_forced_fwd = k; }
 static int forced_fwd_kernel() {
-  static const int k = [] {
+  static const int env = [] {
     const char* e = getenv("MIMIC_FWD_KERNEL");
     return e ? atoi(e) : 0;
   }();
-  return k;
+  return g_forced_fwd >= 0 ? g_forced_fwd : env;
 }
 static bool env_flag(const char* name) { return getenv(name) != nullptr; }
 
 int fwd(const AttnParams& p, cudaStream_t st) {
   static const bool no_persistent = env_flag("MIMIC_NO_PERSISTENT");
   const int forced = forced_fwd_kernel();
-  if ((forced == 0 || forced == 6) && fwdp_supports(p)) return fwdp(p, st);
+  if ((forced == 0 || forced == 6) && fwdp_supports(p, forced == 6)) return fwdp(p, st);
   const int kern = (forced == 0 || forced == 6) ? 3 : forced;
   if (kern == 5 && (size_t)((p.S + 63) / 64) * 8 < 8000) return fwd64w(p, st);   // experimental, never picked by default
   if ((kern == 3 || kern == 4) && (size_t)((p.S + 63) / 64) * 8 < 16000) {

@@ -24,7 +24,6 @@
 #include <cuda.h>
 
 #include <atomic>
-#include <cstdlib>
 
 #include "attn_common.cuh"
 #include "tc_host.cuh"
@@ -98,7 +97,7 @@ struct FwdCounts {       // what the MMA issuer needs of an item
 __global__ void __launch_bounds__(fp::THREADS, 1)
 attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, AttnParams p,
-                    int sec_hb, unsigned int* ticket, int static_sched) {
+                    int sec_hb, unsigned int* ticket) {
   using namespace fp;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -268,7 +267,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (!pub_done) {
           const int slot = pub % NSCHED;
           if (pub < (uint32_t)NSCHED || mbar_test_wait(&bars[SCHED_EMPTY + slot], ((pub / NSCHED) & 1) ^ 1)) {
-            const int it = static_sched ? (int)(blockIdx.x + pub * gridDim.x) : (int)atomicAdd(ticket, 1u);
+            const int it = (int)atomicAdd(ticket, 1u);
             sched[slot] = it;
             mbar_arrive(&bars[SCHED_FULL + slot]);           // release: the store above is visible to the waiters
             ++pub;
@@ -311,7 +310,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       // the last CTA to run out of work re-arms the ticket counter for the next launch that uses it
       __threadfence();
-      if (!static_sched && atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
+      if (atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
         ticket[0] = 0u;
         ticket[1] = 0u;
         __threadfence();
@@ -837,9 +836,12 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
-bool fwdp_supports(const AttnParams& p) {
+bool fwdp_supports(const AttnParams& p, bool forced) {
   using namespace fp;
-  if (p.T <= BM) return false;                                  // one query tile: the single-tile kernels
+  // Measured on B200 (scripts/ab_fwd.py, MIMIC_FWD_KERNEL=6 vs 3): ahead of the 64-key kernels from ~2k query rows per
+  // (head, batch) on (+8 % at the Idefics2 context pass, +11 % at T = 8192), level at 2048, behind below (few key tiles
+  // per item: the item hand-over weighs more than the 128-key MMAs save)
+  if (p.T <= BM || (!forced && p.T < 2048)) return false;   // (one query tile: the single-tile kernels)
   if (p.key_mask != nullptr && (size_t)p.B * kbit_words(p.S) * 4 > (size_t)KBITS_MAX) return false;
   return true;
 }
@@ -873,8 +875,7 @@ int fwdp(const AttnParams& p, cudaStream_t st) {
   unsigned int* tickets = nullptr;
   MIMIC_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_fwdp_tickets));
   unsigned int* ticket = tickets + 2 * (seq.fetch_add(1) % N_TICKETS);
-  static const int static_sched = getenv("MIMIC_FWDP_STATIC") ? 1 : 0;       // A/B only: round-robin instead of tickets
-  attn_fwd_tcp_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec, ticket, static_sched);
+  attn_fwd_tcp_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec, ticket);
   MIMIC_LAUNCH_OK("attn_fwd_tcp_kernel");
   return MIMIC_OK;
 }

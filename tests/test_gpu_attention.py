@@ -171,3 +171,51 @@ def _make_encoder(lmm):
     from mimic_b200 import AttnApproximator
     return AttnApproximator(lmm, "ShiftStrategy.VECTOR_SHIFT | ShiftStrategy.LEARNABLE_SHIFT_SCALE | ShiftStrategy.MULTI_HEAD",
                             "ShiftStrategy.RECORD_HIDDEN_STATES")
+
+
+@pytest.fixture
+def force_ping_pong():
+    """Pin the forward to the persistent ping-pong kernel (the default only picks it from 2048 query rows on)."""
+    from mimic_b200 import _lib
+    _lib.lib.mimic_debug_force_fwd_kernel(6)
+    yield
+    _lib.lib.mimic_debug_force_fwd_kernel(-1)
+
+
+PP_CASES = [c for c in CASES if c[3] > 128 and c[5] == 128] + [
+    # B, H, Hkv, T, S, d, causal, pad, active
+    (2, 4, 2, 384, 384, 128, True, True, True),        # 1.5 pairs of query tiles: the last pair has one tile only
+    (1, 2, 1, 700, 700, 128, True, True, False),       # inactive, ragged, padding holes, GQA 2:1
+    (1, 2, 2, 260, 1000, 128, True, False, True),      # T < S: every tile sees a long fully visible prefix
+    (2, 2, 2, 513, 513, 128, False, True, True),       # non-causal with padding: masked keys are "excluded"
+    (1, 3, 3, 1300, 1300, 128, True, False, True),     # several items per CTA slot when the grid is small
+]
+
+
+@pytest.mark.parametrize("case", PP_CASES, ids=[f"B{c[0]}H{c[1]}kv{c[2]}T{c[3]}S{c[4]}c{int(c[6])}p{int(c[7])}a{int(c[8])}" for c in PP_CASES])
+def test_ping_pong_forward_matches_oracle(case, force_ping_pong):
+    """attn_tc_fwdp.cu on shapes below its dispatch threshold (forced): out / lse / mu and, through the shared backward, the
+    gradients, against the fp32 oracle at the north-star 1e-2."""
+    from mimic_b200 import _lib
+    B, H, Hkv, T, S, d, causal, pad, active = case
+    g = torch.Generator().manual_seed(77 + T + S)
+    rd = lambda t: t.bfloat16().float()
+    q, k, v = rd(torch.randn(B, H, T, d, generator=g)), rd(torch.randn(B, Hkv, S, d, generator=g)), rd(torch.randn(B, Hkv, S, d, generator=g))
+    d_out = rd(torch.randn(B, T, H, d, generator=g))
+    shift, w, b = torch.randn(H, d, generator=g) * 0.5, torch.randn(H, d, generator=g) * 0.2, torch.randn(H, generator=g)
+    km = None
+    if pad:
+        km = torch.ones(B, S, dtype=torch.bool)
+        km[0, :7] = False
+        km[B - 1, S // 2] = False
+        km[B - 1, S // 3: S // 3 + 40] = False          # a hole wider than a 32-key chunk
+        vis = OA.visibility(T, S, B, causal, km).any(-1)[:, 0]
+        d_out = d_out * vis[:, :, None, None]
+    out, grads = run_cuda(q, k, v, shift, w, b, d_out, km, causal, active, torch.bfloat16, impl="tcgen05")
+    assert _lib.last_attn_impl() == "tcgen05"
+    kw = dict(causal=causal, key_mask=km, active=active)
+    want = OA.shifted_attention_fwd(q, k, v, shift, w, b, **kw)["out"]
+    wg = OA.shifted_attention_bwd(q, k, v, shift, w, b, d_out, **kw)
+    assert rel(out, want) < 1e-2, "out"
+    for name, got in grads.items():
+        assert rel(got, wg[name]) < 1e-2, name
