@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libmimic_b200.so")
-SOURCES = ["api.cu", "attn_api.cu", "attn_simt.cu", "attn_tc.cu", "attn_tc_fwd2.cu", "attn_tc_fwd64.cu", "attn_tc_fwd64p.cu", "attn_tc_fwd64w.cu", "attn_tc_fwdp.cu", "attn_tc_bwd.cu", "losses.cu", "norm_shift.cu", "row_plan.cu"]
+SOURCES = ["api.cu", "attn_api.cu", "attn_simt.cu", "attn_tc.cu", "attn_tc_fwd64.cu", "attn_tc_fwd64p.cu", "attn_tc_fwdp.cu", "attn_tc_bwd.cu", "losses.cu", "norm_shift.cu", "row_plan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

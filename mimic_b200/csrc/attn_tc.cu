@@ -445,18 +445,16 @@ bool supports(const AttnParams& p, bool backward) {
   return p.dtype == MIMIC_BF16 && p.d == HD && p.S <= (1 << 18) && p.T >= 1;
 }
 
-int fwd2(const AttnParams& p, cudaStream_t st);   // attn_tc_fwd2.cu: two query tiles per CTA
 int fwd64(const AttnParams& p, cudaStream_t st);  // attn_tc_fwd64.cu: 64-key tiles, two CTAs per SM
 int fwd64p(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64p.cu: the same pipeline in persistent CTAs (static work lists)
-int fwd64w(const AttnParams& p, cudaStream_t st); // attn_tc_fwd64w.cu: eight softmax warps per CTA (opt-in, not yet validated on a GPU)
 
 int fwdp(const AttnParams& p, cudaStream_t st);   // attn_tc_fwdp.cu: persistent, two 128-row query tiles ping-ponged over 128-key tiles
 bool fwdp_supports(const AttnParams& p, bool forced);
 
 // Forward kernel choice.  MIMIC_FWD_KERNEL (read ONCE per process; A/B scripts set it before the first call) forces a family:
-// "1" single-tile / "2" ping-pong, one item per CTA / "3" 64-key tiles, two CTAs per SM (persistent when it pays) /
-// "4" that one persistent always / "5" wide softmax (experiment) / "6" persistent ping-pong.  Default: 6 where it applies
-// (more than one query tile), else 3.
+// "1" single-tile, 128-key tiles / "3" 64-key tiles, two CTAs per SM (persistent when it pays) / "4" that one persistent
+// always / "5" never persistent / "6" persistent ping-pong.  Default: 6 from 2048 query rows on, else 3.  (The one-item-per-CTA ping-pong and
+// the eight-softmax-warp experiments of round 1 were measured slower everywhere and are gone: DESIGN.md §4.)
 static int g_forced_fwd = -1;            // mimic_debug_force_fwd_kernel(); -1 = MIMIC_FWD_KERNEL (read once) or 0
 void force_fwd_kernel(int k) { g_forced_fwd = k; }
 static int forced_fwd_kernel() {
@@ -471,19 +469,23 @@ static bool env_flag(const char* name) { return getenv(name) != nullptr; }
 int fwd(const AttnParams& p, cudaStream_t st) {
   static const bool no_persistent = env_flag("MIMIC_NO_PERSISTENT");
   const int forced = forced_fwd_kernel();
-  if ((forced == 0 || forced == 6) && fwdp_supports(p, forced == 6)) return fwdp(p, st);
+  // persistent 64-key variant applies: inactive handle (context pass), several tiles per CTA slot, AND the K/V of every
+  // (kv head, batch) stream fit the L2 budget together — its CTAs in flight touch all streams at once
+  const long long items64 = (long long)((p.T + 127) / 128) * p.H * p.B;
+  const long long kv_bytes = 2LL * p.B * p.Hkv * p.S * p.d * 2;
+  const bool p64_applies = !p.active && items64 >= 4LL * 2 * num_sms() && kv_bytes <= l2_budget_bytes() &&
+                           (size_t)((p.S + 63) / 64) * 8 < 16000 && !no_persistent;
+  // Ping-pong kernel from 2048 query rows on — except the padded context pass, where the persistent 64-key kernel is
+  // ahead (measured at the Idefics2 shape, padding mask: 727 vs 654 TFLOP/s; without a mask 727 vs 755): the tile that
+  // holds the padding takes the two-pass mixed path in every item of that batch row.
+  const bool prefer_p64 = p.key_mask != nullptr && p64_applies;
+  if (forced == 6 ? fwdp_supports(p, true) : (forced == 0 && !prefer_p64 && fwdp_supports(p, false))) return fwdp(p, st);
   const int kern = (forced == 0 || forced == 6) ? 3 : forced;
-  if (kern == 5 && (size_t)((p.S + 63) / 64) * 8 < 8000) return fwd64w(p, st);   // experimental, never picked by default
-  if ((kern == 3 || kern == 4) && (size_t)((p.S + 63) / 64) * 8 < 16000) {
-    // persistent variant: inactive handle (context pass), several tiles per CTA slot, AND the K/V of every (kv head,
-    // batch) stream fit the L2 budget together — its CTAs in flight touch all streams at once
-    const long long items = (long long)((p.T + 127) / 128) * p.H * p.B;
-    const long long kv_bytes = 2LL * p.B * p.Hkv * p.S * p.d * 2;
-    const bool persistent = kern == 4 || (!p.active && items >= 4LL * 2 * num_sms() && kv_bytes <= l2_budget_bytes());
-    if (persistent && !no_persistent) return fwd64p(p, st);
+  if ((kern == 3 || kern == 4 || kern == 5) && (size_t)((p.S + 63) / 64) * 8 < 16000) {
+    const bool persistent = kern == 4 || p64_applies;
+    if (persistent && !no_persistent && kern != 5) return fwd64p(p, st);
     return fwd64(p, st);
   }
-  if (kern == 2 && p.T > BM) return fwd2(p, st);
   AttnParams pd = p;
   static const int dbg_flags = [] { const char* e = getenv("MIMIC_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
   pd.debug_flags = dbg_flags;

@@ -66,14 +66,7 @@ static_assert(2 * REG_SOFTMAX + REG_EPI + REG_MISC <= 4 * REG_LAUNCH, "register 
 inline int kbit_words(int S) { return ((S + BN - 1) / BN) * 4; }
 }  // namespace fp
 
-// bounded wait without a stack frame: a protocol bug traps instead of hanging the GPU box (no printf here — the format
-// call cost every wait a frame and ~150 cycles; the debug twin of the older kernels keeps it)
-__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
-}
+__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, 0); }
 
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

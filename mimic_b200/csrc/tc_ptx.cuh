@@ -51,16 +51,22 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU box.  ~seconds of spinning, then trap.
+// Bounded wait: a protocol bug must not hang the GPU box — after ~seconds of failed tries the thread traps.  The
+// production build carries NO printf: the format call gave every wait a stack frame and cost the single-thread MMA
+// issuers ~150 cycles per wait even when the phase had completed long ago.  Build with -DMIMIC_MBAR_DEBUG to get the
+// "which barrier, which thread" message back (`tag` identifies the call site).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << 22)) {
+#ifdef MIMIC_MBAR_DEBUG
       printf("[mimic tcgen05] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, parity);
+#endif
       __trap();
     }
   }
+  (void)tag;
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------
