@@ -458,6 +458,229 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
 }
 
 // ---------------------------------------------------------------------------------------------
+// C, register-resident variant (bf16): the logits row never leaves the chip between the statistics and the gradient.
+// A thread-block CLUSTER of CL CTAs x 256 threads owns a row; every thread loads its <= MAXC 16-byte chunks ONCE into
+// registers (raw bf16: 4 registers per chunk), reduces (max, sum) inside its CTA, the CTAs of the cluster exchange their
+// two floats through distributed shared memory (one cluster barrier per row), and the gradient is formed from the same
+// registers and streamed out: dram read == algorithmic (the two-pass kernel re-read 0.36 GB of the 0.47 GB LLaVA logits
+// from HBM: 296 CTAs x 304 KB rows + gradients outgrow L2).  Four CTAs per SM sit in different phases of their rows, so
+// loads, exponentials and stores of neighbouring rows overlap.  CL is the smallest of 1 / 2 / 4 / 8 whose registers hold
+// the row (V <= 20 480 / 40 960 / 81 920 / 163 840); longer rows and fp32 logits take the two-pass kernel above.
+template <int CL>
+__device__ __forceinline__ void cluster_sync_all() {
+  if constexpr (CL > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float2 dsmem_ld_f2(const float2* local, uint32_t cta) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int CE_MAXC = 10;
+constexpr int CE_NT = 256;      // threads per CTA: four CTAs per SM (64 registers each) drift apart in phase and overlap their rows
+
+template <int CL>
+__global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_kernel(const __nv_bfloat16* __restrict__ logits, int64_t row_stride,
+                                                                const int64_t* __restrict__ labels, __nv_bfloat16* dlogits,
+                                                                float grad_scale, int R, int V, int32_t* __restrict__ n_kept,
+                                                                float* __restrict__ loss, float* __restrict__ row_loss,
+                                                                unsigned int* __restrict__ counter) {
+  using T = __nv_bfloat16;
+  __shared__ float red[32];
+  __shared__ float bc[2];
+  __shared__ float2 xchg[2];               // this CTA's (max, sum) of a row, double-buffered by processed-row parity
+  __shared__ bool is_last;
+  constexpr float L2E = 1.4426950408889634f;
+  const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int gtid = rank * CE_NT + threadIdx.x;
+  constexpr int GT = CL * CE_NT;
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += labels[i] >= 0 ? 1.f : 0.f;
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) bc[0] = cnt;
+  __syncthreads();
+  const float n_keep = bc[0];
+  __syncthreads();
+  const float inv_n = n_keep > 0.f ? 1.f / n_keep : 0.f;
+  const float gs = grad_scale * inv_n;
+  uint32_t done = 0;                       // rows this cluster has put through the exchange (slot parity)
+  // (Tried and measured slower, 0.51 vs 0.63 of the HBM peak: prefetching chunk u of the cluster's next row into the
+  // registers of chunk u as soon as its gradient is stored — the interleaved loads and stores of one warp get in each
+  // other's way.  Rows are loaded at the top of their iteration; the two CTAs of an SM provide the overlap.)
+  for (int r = cluster_id; r < R; r += n_clusters) {
+    const T* x = logits + (int64_t)r * row_stride;
+    T* dx = dlogits ? dlogits + (int64_t)r * row_stride : nullptr;
+    const int64_t label = labels[r];
+    const int head = head_elems(x, V);
+    const int body = (V - head) / 8;
+    const int tail0 = head + body * 8;
+    if (label < 0) {                       // (uniform over the cluster: no barrier on this path)
+      if (gtid == 0) row_loss[r] = 0.f;
+      if (dx) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = gtid; i < head; i += GT) dx[i] = from_f32<T>(0.f);
+        for (int c = gtid; c < body; c += GT) Chunk<T>::store(dx + head + c * 8, z);
+        for (int i = tail0 + gtid; i < V; i += GT) dx[i] = from_f32<T>(0.f);
+      }
+      continue;
+    }
+    // ---- the row, once: <= MAXC chunks per thread, all loads in flight before the first use ----
+    Raw8<T> raw[CE_MAXC];
+#pragma unroll
+    for (int u = 0; u < CE_MAXC; ++u) {
+      const int c = gtid + u * GT;
+      if (c < body) raw[u].u = ldg_stream(x + head + c * 8);
+    }
+    // the <= 7 + 7 elements in front of / behind the 16-byte aligned body: one each for the first threads of the cluster
+    const int ei = gtid < head ? gtid : (gtid >= 32 && gtid < 40 && tail0 + (gtid - 32) < V ? tail0 + gtid - 32 : -1);
+    const float ex = ei >= 0 ? to_f32(x[ei]) : -INFINITY;
+    float m = ex;
+#pragma unroll
+    for (int u = 0; u < CE_MAXC; ++u) {
+      if (gtid + u * GT < body) {
+        float f[8];
+        raw[u].unpack(f);
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7]))));
+      }
+    }
+    // e = exp2((x - m_thread) log2e): summed in fp32, then written back over the raw chunk as bf16 pairs — the gradient
+    // pass multiplies it by a per-thread factor instead of exponentiating again (ONE MUFU per element, the kernel was
+    // issue / MUFU bound at two; the extra rounding is below the bf16 rounding of the gradient itself)
+    float s = 0.f, ee = 0.f;
+    {
+      const float nm = (m == -INFINITY) ? 0.f : -m * L2E;
+      if (ei >= 0) {
+        ee = fast_ex2(fmaf(ex, L2E, nm));
+        s += ee;
+      }
+#pragma unroll
+      for (int u = 0; u < CE_MAXC; ++u) {
+        if (gtid + u * GT < body) {
+          float f[8];
+          raw[u].unpack(f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = fast_ex2(fmaf(f[e], L2E, nm));
+            s += f[e];
+          }
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw[u].u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        }
+      }
+    }
+    // ---- CTA (max, sum), then the cluster's ----
+    float gm = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    gm = red[0];
+#pragma unroll
+    for (int wi = 1; wi < CE_NT / 32; ++wi) gm = fmaxf(gm, red[wi]);
+    float ss = (m == -INFINITY) ? 0.f : s * fast_ex2((m - gm) * L2E);
+    ss = block_sum(ss, red);
+    const int par = done & 1;
+    if (threadIdx.x == 0) xchg[par] = make_float2(gm, ss);
+    cluster_sync_all<CL>();
+    float M = -INFINITY, Ssum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CL; ++c) {
+      const float2 v = CL > 1 ? dsmem_ld_f2(&xchg[par], (uint32_t)c) : xchg[par];
+      const float Mn = fmaxf(M, v.x);
+      Ssum = Ssum * ((M == -INFINITY) ? 0.f : fast_ex2((M - Mn) * L2E)) + v.y * fast_ex2((v.x - Mn) * L2E);
+      M = Mn;
+    }
+    ++done;
+    const float lse = M + __logf(Ssum);
+    if (gtid == 0) row_loss[r] = lse - to_f32(x[label]);
+    // ---- gradient from the same registers: p = e * exp2((m_thread - lse) log2e), one multiply per element ----
+    const float fac = (m == -INFINITY) ? 0.f : gs * fast_ex2((m - lse) * L2E);
+    if (dx && ei >= 0) dx[ei] = from_f32<T>(ee * fac - (ei == (int)label ? gs : 0.f));
+    const int lab_c = ((int)label - head) >> 3;             // chunk that holds the label (only it pays the compare)
+#pragma unroll
+    for (int u = 0; u < CE_MAXC; ++u) {
+      const int c = gtid + u * GT;
+      if (dx && c < body) {
+        float f[8];
+        raw[u].unpack(f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] *= fac;
+        if (c == lab_c && (int)label >= head) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (head + c * 8 + e == (int)label) f[e] -= gs;
+        }
+        Chunk<T>::store(dx + head + c * 8, f);
+      }
+    }
+  }
+  cluster_sync_all<CL>();                   // no CTA leaves while a neighbour may still read its exchange slot
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      loss[0] = tot * inv_n;
+      n_kept[0] = (int32_t)(n_keep + 0.5f);
+      *counter = 0u;
+    }
+  }
+}
+
+template <int CL>
+static int launch_ce_reg(const __nv_bfloat16* logits, int64_t row_stride, const int64_t* labels, __nv_bfloat16* dlogits,
+                         float grad_scale, int R, int V, int32_t* n_kept, float* loss, float* row_loss, unsigned int* counter,
+                         cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(CE_NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent clusters: exactly as many as the device co-schedules (a cluster that has to wait for a second wave would
+  // start its static share of the rows when the others are done — measured: 74 launched, 71 resident, SMs 33 % idle)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(CL * num_sms() * 4);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ce_fwd_bwd_reg_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = num_sms() * (65536 / (CE_NT * 64)) / CL - 4;
+    max_clusters = n > 0 ? n : 1;
+  }
+  int n_clusters = max_clusters < R ? max_clusters : R;
+  cfg.gridDim = dim3(n_clusters * CL);
+  MIMIC_CUDA_OK(cudaLaunchKernelEx(&cfg, ce_fwd_bwd_reg_kernel<CL>, logits, row_stride, labels, dlogits, grad_scale, R, V,
+                                   n_kept, loss, row_loss, counter));
+  return MIMIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Layer-wise cosine-similarity alignment (Strategy.LAYER_WISE_COS_SIM, src/shift_model.py:152-160), forward +
 // backward in one launch.  One CTA per (layer, row) item keeps the row of H and H' in registers between the
 // reduction (h.h', |h|^2, |h'|^2) and the gradient, so HBM is read once:  3 * N * sizeof(T) algorithmic bytes, as M.
@@ -1133,6 +1356,21 @@ extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, i
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
   float* row_loss = static_cast<float*>(workspace) + 4;
   const int grid = R < num_sms() * 4 ? R : num_sms() * 4;   // measured: more CTAs beat a smaller L2 footprint
+  static const bool two_pass_only = getenv("MIMIC_CE_TWO_PASS") != nullptr;      // A/B only
+  if (dtype == MIMIC_BF16 && !two_pass_only && V <= 8 * CE_NT * CE_MAXC * 8) {
+    // register-resident row: the smallest cluster whose registers hold it (7 elements of slack for the unaligned head)
+    const __nv_bfloat16* lg = (const __nv_bfloat16*)logits;
+    __nv_bfloat16* dl = (__nv_bfloat16*)dlogits;
+    const int64_t cap1 = (int64_t)CE_NT * CE_MAXC * 8;
+    int rc;
+    if (V <= cap1) rc = launch_ce_reg<1>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
+    else if (V <= 2 * cap1) rc = launch_ce_reg<2>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
+    else if (V <= 4 * cap1) rc = launch_ce_reg<4>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
+    else rc = launch_ce_reg<8>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
+    if (rc) return rc;
+    MIMIC_LAUNCH_OK("ce_fwd_bwd_reg_kernel");
+    return MIMIC_OK;
+  }
   if (dtype == MIMIC_BF16)
     ce_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)logits, logits_row_stride, labels,
                                                            (__nv_bfloat16*)dlogits, grad_scale, R, V, n_kept, loss, row_loss, counter);

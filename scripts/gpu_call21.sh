@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_losses.py tests/test_gpu_fullsize.py tests/test_gpu_tiny_step.py -q -x 2>&1 | grep -v "^$" | tail -12 > gpurun_out/r02_c21_tests.log
+echo "tests rc=${PIPESTATUS[0]}" >> gpurun_out/r02_c21_tests.log
+tail -3 gpurun_out/r02_c21_tests.log
+timeout 300 python scripts/kernel_sweep.py hbm > gpurun_out/r02_c21_hbm.log 2>&1; echo "hbm rc=$?"
