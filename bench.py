@@ -374,6 +374,14 @@ def main():
     ms_eager, _ = timed(step_eager, n_eager)
     ops.timer.enabled = False
     ksum = ops.timer.summary()
+    # who waits for whom: the device time of the all-reduce on each rank (launch to completion, eager steps) — the rank that
+    # arrives last waits least; a uniform, small number means the ~1 MB collective itself is what the step pays
+    ar_ranks = None
+    if world > 1:
+        mine = torch.tensor([ksum.get("nccl_allreduce_grads", (0, 0.0, 0.0))[1]], device=dev)
+        allar = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allar, mine)
+        ar_ranks = [float(x) for x in allar]
 
     tokens_per_step = B * (S + T) * world
     value = tokens_per_step / (ms / args.steps / 1e3)
@@ -426,6 +434,7 @@ def main():
         "tokens_per_s_per_gpu": value / world, "losses": scal,
         "per_rank_ms_per_step": [m / args.steps for m in ms_ranks],
         "per_rank_e2e_ms_per_step": [m / args.steps for m in ms_e2e_ranks],
+        "per_rank_allreduce_ms_eager": ar_ranks,
         "native_library": os.path.relpath(mimic_b200._lib.LIB_PATH, ROOT),
     }
     if world == 1:

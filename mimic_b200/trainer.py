@@ -155,7 +155,9 @@ class MimicTrainer:
 
     def _device_optimizer_step(self) -> None:
         if self.world > 1:
+            _ev = ops.timer.start("nccl_allreduce_grads")                   # (events only when the bench asks for them)
             dist.all_reduce(self.flat.grad_and_scalars, group=self.pg)      # the only collective of the path
+            ops.timer.stop(_ev)
         ops.adamw_step(self.flat.param, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq,
                        self.flat.weight_decay, self.hyper, grad_mul=1.0 / self.world,
                        max_norm=self.clip, sumsq=self.sumsq, lr_mul=self.flat.lr_mul)

@@ -5,14 +5,19 @@ sys.path.insert(0, ".")
 from mimic_b200 import ops
 
 d, H = 128, 32
-# context-pass forward (Idefics2 step shape): B=2, S=3200, GQA 32:8, inactive
+# context-pass forward (Idefics2 step shape): B=2, S=3200, GQA 32:8, inactive, WITH the left-padding mask of the bench batch
+# (persistent 64-key kernel) and without it (persistent ping-pong kernel)
 q = torch.randn(2, H, 3200, d, device="cuda").bfloat16()
 k, v = (torch.randn(2, 8, 3200, d, device="cuda").bfloat16() for _ in range(2))
+km = torch.ones(2, 3200, dtype=torch.bool, device="cuda")
+km[1, :13] = False
+for _ in range(3):
+    ops.shifted_attention_forward(q, k, v, km, None, None, None, causal=True, active=False, scale=d ** -0.5)
 for _ in range(3):
     ops.shifted_attention_forward(q, k, v, None, None, None, None, causal=True, active=False, scale=d ** -0.5)
-# sweep shape, active forward + backward: B=2, T=4096, MHA
-q, k, v = (torch.randn(2, H, 4096, d, device="cuda").bfloat16() for _ in range(3))
-do = torch.randn(2, 4096, H, d, device="cuda").bfloat16()
+# BASELINE config 5, T = 4096 (B = 4, MHA), active forward (persistent ping-pong kernel) + backward
+q, k, v = (torch.randn(4, H, 4096, d, device="cuda").bfloat16() for _ in range(3))
+do = torch.randn(4, 4096, H, d, device="cuda").bfloat16()
 sh, w, b = torch.randn(H, d, device="cuda"), torch.randn(H, d, device="cuda") * 0.1, torch.randn(H, device="cuda")
 for _ in range(3):
     out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, None, sh, w, b, causal=True, active=True, scale=d ** -0.5)
@@ -48,5 +53,15 @@ qv, kv_ = qkv[..., : 32 * 128].view(2, 3200, 32, 128), qkv[..., 32 * 128: 40 * 1
 cs = torch.randn(2, 3200, 128, device="cuda").bfloat16()
 for _ in range(3):
     ops.rope_qk(qv, kv_, cs, cs)
+# kernel P (row plan) and kernel R (record gather) at the step shapes
+ids = torch.randint(3, 32000, (2, 3200), device="cuda")
+ids[:, 1000] = 0
+ids[:, 3100] = 0
+for _ in range(3):
+    plan = ops.row_plan(ids, pad_id=0, bos_id=1, left_padding=True, num_separator=1, select="label", cap=256)
+src = torch.randn(2, 3200, 4096, device="cuda").bfloat16()
+dst = torch.empty(256, 4096, device="cuda", dtype=torch.bfloat16)
+for _ in range(3):
+    ops.record_gather(src, plan.rows, dst)
 torch.cuda.synchronize()
 print("ok")
