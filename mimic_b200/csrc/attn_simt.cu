@@ -225,103 +225,146 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnParams p) {
 //   dmu = g.shift[h]   Delta = g.SA = g.out - mu*dmu   dz = mu(1-mu)dmu
 //   Delta' = Delta + dz*exp(lse_c - lse_full)   (folds the visible part of -dz*P^f into P^c(dP-Delta'))
 //   dq_acc = dz * w[h]      dshift[h] += sum_t mu_t g_t    dw[h] += sum_t dz_t q_t    db[h] += sum_t dz_t
-// Reductions: warp shuffle per row, then per-CTA column sums, then ONE atomicAdd per (CTA, h, c).
-// ROWS query rows per CTA: 64 for long sequences (few atomics per parameter), 16 when the whole problem is a few
-// thousand rows (a MimIC query pass: T = 128) and the launch is pure latency — 4x the CTAs, a quarter of the serial
-// row batches per CTA.
+// ONE pass over g, out and q: a warp owns a query row at a time (a lane its EPL consecutive columns, vector loads, four
+// rows in flight), reduces the two row dots by shuffles, and — because every lane ends up with the row's mu and dz — adds
+// its columns of mu*g and dz*q to per-lane column accumulators on the spot.  (The first version made a second pass over g
+// and q, column-wise per thread, for these sums: 0.27 ms at the T = 4096 sweep shape, a tenth of the whole backward, against
+// ~0.1 ms for its bytes.)  Per CTA: the four warps' column sums meet in shared memory, ONE atomicAdd per (CTA, h, c).
+// ROWS query rows per CTA: 64 for long sequences (few atomics per parameter), 16 when the whole problem is a few thousand
+// rows (a MimIC query pass: T = 128) and the launch is pure latency.
+template <typename E, int EPL>
+__device__ __forceinline__ void load_epl(const E* p, float (&f)[EPL]) {
+  if constexpr (sizeof(E) == 2 && EPL == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  } else if constexpr (sizeof(E) == 2 && EPL == 2) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    f[0] = a.x; f[1] = a.y;
+  } else if constexpr (sizeof(E) == 4 && EPL == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  } else if constexpr (sizeof(E) == 4 && EPL == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    f[0] = a.x; f[1] = a.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) f[e] = to_f32(p[e]);
+  }
+}
+
+// EPL consecutive elements of a row kept in their storage format until use (bf16: half the registers of fp32 — the four
+// rows x three arrays in flight per lane are what decides this kernel's occupancy)
+template <typename E, int EPL>
+struct RawEpl {
+  E v[EPL];
+  __device__ __forceinline__ void load(const E* p) {
+    if constexpr (sizeof(E) * EPL == 8) *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(p);
+    else if constexpr (sizeof(E) * EPL == 16) *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(p);
+    else if constexpr (sizeof(E) * EPL == 4) *reinterpret_cast<uint32_t*>(v) = *reinterpret_cast<const uint32_t*>(p);
+    else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) v[e] = p[e];
+    }
+  }
+  __device__ __forceinline__ float get(int e) const { return to_f32(v[e]); }
+};
+
 template <typename E, int D, int ROWS>
-__global__ void __launch_bounds__(128) attn_bwd_prep_kernel(AttnParams p) {
-  __shared__ float mu_s[ROWS], dz_s[ROWS];
+__global__ void __launch_bounds__(128, 6) attn_bwd_prep_kernel(AttnParams p) {
+  constexpr int EPL = D / 32;  // elements per lane
+  __shared__ float col_s[4][D], col_w[4][D];
+  __shared__ float bias_s[4];
   const int t0 = blockIdx.x * ROWS, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = p.T;
-  constexpr int EPL = D / 32;  // elements per lane
-  const E* gb = reinterpret_cast<const E*>(p.d_out) + b * p.go_sb + h * p.go_sh;
-  const E* ob = reinterpret_cast<const E*>(p.out) + b * p.o_sb + h * p.o_sh;
-  const E* qb = reinterpret_cast<const E*>(p.q) + b * p.q_sb + h * p.q_sh;
+  const int c0 = lane * EPL;
+  const E* gb = reinterpret_cast<const E*>(p.d_out) + b * p.go_sb + h * p.go_sh + c0;
+  const E* ob = reinterpret_cast<const E*>(p.out) + b * p.o_sb + h * p.o_sh + c0;
+  const E* qb = reinterpret_cast<const E*>(p.q) + b * p.q_sb + h * p.q_sh + c0;
   const int64_t row0 = ((int64_t)b * p.H + h) * T;
-
-  // rows r = warp + 4 i: four rows per batch, all their loads issued before the first reduction (a launch at T = 128 is
-  // pure latency: 16 serial row trips per warp cost more than the tensor-core kernel that follows)
+  float shv[EPL], wv[EPL], acc_s[EPL], acc_w[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    shv[e] = p.active ? p.shift[h * D + c0 + e] : 0.f;
+    wv[e] = p.active ? p.w[h * D + c0 + e] * p.dq_seed_mul : 0.f;
+    acc_s[e] = 0.f;
+    acc_w[e] = 0.f;
+  }
+  float acc_b = 0.f;
+  // rows r = warp + 4 i of the CTA's block, four at a time: all their loads are issued before the first reduction
   for (int r4 = 0; r4 < ROWS / 4; r4 += 4) {
-    float gv[4][EPL], ov[4][EPL];
+    RawEpl<E, EPL> gv[4], ov[4], qv[4];
+    float mu4[4], rho4[4], dl4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 + warp + 4 * (r4 + i);
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const int c = lane * EPL + e;
-        gv[i][e] = t < T ? to_f32(gb[(int64_t)t * p.go_st + c]) : 0.f;
-        ov[i][e] = t < T ? to_f32(ob[(int64_t)t * p.o_st + c]) : 0.f;
+      const bool in = t < T;
+      const int tc = in ? t : T - 1;                       // clamped: no branch around the loads, results masked below
+      gv[i].load(gb + (int64_t)tc * p.go_st);
+      ov[i].load(ob + (int64_t)tc * p.o_st);
+      if (p.active) {
+        qv[i].load(qb + (int64_t)tc * p.q_st);
+        mu4[i] = p.mu[row0 + tc];                          // (the same address in every lane: one broadcast load)
+        rho4[i] = p.lse_c[row0 + tc] - p.lse_full[row0 + tc];
+        dl4[i] = p.d_lse_full ? p.d_lse_full[row0 + tc] : 0.f;
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = warp + 4 * (r4 + i);
-      const int t = t0 + r;
+      const int t = t0 + warp + 4 * (r4 + i);
+      const bool in = t < T;
       float dmu = 0.f, gout = 0.f;
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
-        gout += gv[i][e] * ov[i][e];
-        if (p.active) dmu += gv[i][e] * p.shift[h * D + lane * EPL + e];
+        gout += gv[i].get(e) * ov[i].get(e);
+        dmu += gv[i].get(e) * shv[e];
       }
-      dmu = warp_sum(dmu);
+      dmu = warp_sum(dmu);                                 // (xor shuffles: every lane holds the row's sums)
       gout = warp_sum(gout);
-      if (lane == 0) {
-        float mu = 0.f, dz = 0.f, dl = 0.f;
-        if (t < T) {
-          if (p.active) {
-            mu = p.mu[row0 + t];
-            dz = mu * (1.f - mu) * dmu;
-            // a gradient g arriving at lse_full itself adds g * P^f to dS, i.e. acts like dz = -g on the score path only
-            // (it has no z1 = q.W + b behind it, so the parameter / dq-seed sums below keep the op's own dz)
-            const float dz_all = dz - (p.d_lse_full ? p.d_lse_full[row0 + t] : 0.f);
-            const float lc = p.lse_c[row0 + t];
-            const float rho = (lc == -INFINITY) ? 0.f : expf(lc - p.lse_full[row0 + t]);
-            dl = gout - mu * dmu + dz_all * rho;
-            p.dz_ws[row0 + t] = dz_all;
-          } else {
-            dl = gout;
-            p.dz_ws[row0 + t] = 0.f;
-          }
+      float mu = 0.f, dz = 0.f, dl = gout, dz_all = 0.f;
+      if (p.active) {
+        mu = mu4[i];
+        dz = mu * (1.f - mu) * dmu;
+        // a gradient g arriving at lse_full itself adds g * P^f to dS, i.e. acts like dz = -g on the score path only
+        // (it has no z1 = q.W + b behind it, so the parameter / dq-seed sums below keep the op's own dz)
+        dz_all = dz - dl4[i];
+        const float rho = (rho4[i] != rho4[i] || rho4[i] == -INFINITY) ? 0.f : expf(rho4[i]);   // lse_c = -inf: no visible key
+        dl = gout - mu * dmu + dz_all * rho;
+      }
+      if (in) {
+        if (lane == 0) {
+          p.dz_ws[row0 + t] = dz_all;
           p.delta_ws[row0 + t] = dl;
         }
-        mu_s[r] = mu;
-        dz_s[r] = dz;
+        float* dqa = p.dq_acc + (row0 + t) * D + c0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) dqa[e] = dz * wv[e];   // dq seed (zero for an inactive handle)
+        if (p.active) {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            acc_s[e] = fmaf(mu, gv[i].get(e), acc_s[e]);
+            acc_w[e] = fmaf(dz, qv[i].get(e), acc_w[e]);
+          }
+          acc_b += dz;
+        }
       }
     }
   }
-  __syncthreads();
-  if (tid < D) {
-    const int c = tid;
-    float acc_s = 0.f, acc_w = 0.f;
-    const float wv = p.active ? p.w[h * D + c] : 0.f;
-    for (int r0 = 0; r0 < ROWS; r0 += 8) {               // eight rows of g and q in flight per thread
-      float g8[8], q8[8];
+  if (p.active) {                                          // (kernel-uniform)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int t = t0 + r0 + i;
-        const bool in = p.active && t < T;
-        g8[i] = in ? to_f32(gb[(int64_t)t * p.go_st + c]) : 0.f;
-        q8[i] = in ? to_f32(qb[(int64_t)t * p.q_st + c]) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + i, t = t0 + r;
-        if (t < T) p.dq_acc[(row0 + t) * D + c] = dz_s[r] * wv * p.dq_seed_mul;
-        acc_s += mu_s[r] * g8[i];
-        acc_w += dz_s[r] * q8[i];
-      }
+    for (int e = 0; e < EPL; ++e) {
+      col_s[warp][c0 + e] = acc_s[e];
+      col_w[warp][c0 + e] = acc_w[e];
     }
-    if (p.active) {
-      atomicAdd(p.dshift + h * D + c, acc_s);
-      atomicAdd(p.dw + h * D + c, acc_w);
+    if (lane == 0) bias_s[warp] = acc_b;
+    __syncthreads();
+    if (tid < D) {
+      atomicAdd(p.dshift + h * D + tid, (col_s[0][tid] + col_s[1][tid]) + (col_s[2][tid] + col_s[3][tid]));
+      atomicAdd(p.dw + h * D + tid, (col_w[0][tid] + col_w[1][tid]) + (col_w[2][tid] + col_w[3][tid]));
     }
-  }
-  if (p.active && tid == 127) {
-    float sdz = 0.f;
-    for (int r = 0; r < ROWS; ++r) sdz += dz_s[r];
-    atomicAdd(p.dbias + h, sdz);
+    if (tid == 127) atomicAdd(p.dbias + h, (bias_s[0] + bias_s[1]) + (bias_s[2] + bias_s[3]));
   }
 }
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(bw::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
-                   const __grid_constant__ CUtensorMap tm_dq, AttnParams p) {
+                   const __grid_constant__ CUtensorMap tm_dq, AttnParams p, int debug_life) {
   using namespace bw;
   // address the dynamic window directly (no pointer rounding through integers): keeps every access LDS/STS
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -94,6 +94,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   };
   auto dbg = [&](int bit) { return DBG && (p.debug_flags & bit) != 0; };
+  // per-CTA life cycle (debug): trace[2048 + 8 cta + k] = SM id / entry / prologue done / K,V landed / last MMA done (DKV_FULL
+  // seen) / dK,dV stores issued / exit, in nanoseconds of %globaltimer — where do the ~17 us a CTA costs beyond its iterations go?
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  auto life = [&](int k) {
+    if constexpr (DBG) {
+      if (p.trace != nullptr && debug_life) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[2048 + 8 * cta_lin + k] = t;
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    if constexpr (DBG) {
+      if (p.trace != nullptr && debug_life) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[2048 + 8 * cta_lin] = smid;
+      }
+    }
+    life(1);
+  }
   const int G = p.H / p.Hkv;
   const int T = p.T, S = p.S, off = p.S - p.T;
   const int s0 = kt * BN;
@@ -136,6 +158,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) life(2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -192,6 +215,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t ds_mn0 = desc_lo(smem_u32(sDS), 16);
       auto next_qt = [&](int qt) { return qt + 1 == n_qt ? qt_first : qt + 1; };
       mbar_wait(&bars[KV_FULL], 0, 200);
+      if (warp == 1 && lane == 0) life(3);
       if (warp == 22) {
         // ---------------- issuer B: S^T / dP^T of iteration i2 = 0 .. n-1 ----------------
         int qt2 = qt_first, qs2 = 0, qph2 = 0;
@@ -468,6 +492,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(&bars[DKV_FULL], 0, 330);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) life(4);
     {
       // dV / dK leave through shared memory (the K and V tiles are dead once DKV_FULL fired) and four TMA tile stores:
       // thread-per-row global stores touch 32 different lines per warp instruction (~4000 sector writes per CTA).
@@ -502,7 +527,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tma_store_4d(&tm_dk, sK, 0, s0, kvh, b);
         tma_store_4d(&tm_dk, sK + KV_HALF, 64, s0, kvh, b);
         bulk_commit();
+        life(5);
         bulk_wait_read0();
+        life(6);
       }
     }
     tc_fence_before();
@@ -559,6 +586,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+    if (lane == 0) life(7);
   }
 }
 
@@ -571,7 +599,8 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   pp.dq_seed_mul = 1.f / p.scale;
   pp.dq_out_mul = p.scale;
   pp.trace = debug_trace_capacity() >= 24 * 64 ? debug_trace_buffer() : nullptr;
-  if (const char* e = getenv("MIMIC_DEBUG_FLAGS")) pp.debug_flags = atoi(e);   // bit 0: skip the dQ reduce (timing experiments only)
+  static const int dbg_env = [] { const char* e = getenv("MIMIC_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();   // bit 0: skip the dQ reduce (timing experiments only)
+  pp.debug_flags = dbg_env;
   if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
   CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   if ((rc = make_map_f32_rows(&tdq, p.dq_acc, (int64_t)p.B * p.H, p.T, 16))) return rc;
@@ -589,8 +618,9 @@ int bwd(const AttnParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((p.S + BN - 1) / BN, p.Hkv, p.B);
-  if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp);
-  else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp);
+  const int life = debug_trace_capacity() >= 2048 + 8 * (size_t)grid.x * grid.y * grid.z ? 1 : 0;
+  if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp, life);
+  else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp, 0);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
   return simt::convert_dq_bf16(pp, st);
 }
