@@ -203,6 +203,50 @@ def attention_sweep(peaks, *, reps=20, warm=3, with_reference=True):
     return out
 
 
+def query_pass_in_graph(n_calls=200):
+    """The query-pass attention of config 2 (B = 2, H = 32, Hkv = 8, T = S = 128, active = 1) as the step runs it: inside
+    a CUDA graph.  n_calls calls captured back to back, one pair of events around a replay -> us per call (all launches of
+    the op: forward = 1, backward = prep + main + dq conversion).  `own_kernels` above times the same ops eagerly, events
+    around each call, launch gaps included."""
+    import torch
+    from mimic_b200 import ops
+    dev, d, B, H, Hkv, T = "cuda", 128, 2, 32, 8, 128
+    g = torch.Generator(device=dev).manual_seed(1)
+    q = torch.randn(B, H, T, d, device=dev, generator=g).bfloat16()
+    k, v = (torch.randn(B, Hkv, T, d, device=dev, generator=g).bfloat16() for _ in range(2))
+    do = torch.randn(B, T, H, d, device=dev, generator=g).bfloat16()
+    sh, w = torch.randn(H, d, device=dev, generator=g), torch.randn(H, d, device=dev, generator=g) * 0.1
+    b = torch.randn(H, device=dev, generator=g)
+    kw = dict(causal=True, active=True, scale=d ** -0.5, impl="tcgen05")
+    o, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, None, sh, w, b, **kw)
+    res = {"shape": "B=2 H=32 Hkv=8 T=S=128 d=128 active=1 bf16", "calls_per_graph": n_calls}
+    for name, fn in (("attn_bwd_active_T128_S128_us", lambda: ops.shifted_attention_backward(saved, o, do, lse_c, lse_f, mu, **kw)),
+                     ("attn_fwd_active_T128_S128_us", lambda: ops.shifted_attention_forward(q, k, v, None, sh, w, b, **kw))):
+        gr, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gr, stream=st):
+                for _ in range(n_calls):
+                    fn()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            gr.replay()
+        best = None
+        for _ in range(5):
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            gr.replay()
+            e.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(e) / n_calls * 1e3
+            best = us if best is None else min(best, us)
+        res[name] = best
+        del gr
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -456,6 +500,7 @@ def main():
             trainer._graph = None
             torch.cuda.empty_cache()
             line["sweep"] = attention_sweep(peaks, with_reference=not args.no_gpu_reference)
+            line["query_pass_in_graph"] = query_pass_in_graph()
             best = max(line["sweep"], key=lambda r: r["T"] == 4096)
             line["roofline_shifted"] = {"kernel": "shifted_attn_fwd tcgen05, active=1, causal, T=S=4096, B=4, H=32, d=128 (timed alone)",
                                         "bound": "tensor", "achieved": best["fwd_tflops"], "peak": peaks["tf_burst"],

@@ -831,10 +831,11 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 bool fwdp_supports(const AttnParams& p, bool forced) {
   using namespace fp;
-  // Measured on B200 (scripts/ab_fwd.py, MIMIC_FWD_KERNEL=6 vs 3): ahead of the 64-key kernels from ~2k query rows per
-  // (head, batch) on (+8 % at the Idefics2 context pass, +11 % at T = 8192), level at 2048, behind below (few key tiles
-  // per item: the item hand-over weighs more than the 128-key MMAs save)
-  if (p.T <= BM || (!forced && p.T < 2048)) return false;   // (one query tile: the single-tile kernels)
+  // Measured on B200 (scripts/ab_fwd.py, family 6 vs 3, TFLOP/s, B = 16384 / T, H = 32): active handle 372 / 395 at T = 512,
+  // 563 / 546 at 1024, 748 / 726 at 2048, 893 / 857 at 4096, 963 / 894 at 8192; inactive 491 / 534 at 1024, 684 / 707 at 2048,
+  // 871 / 855 at 4096, 1052 / 957 at 8192, 756 / 727 at the Idefics2 context pass (S = 3200, GQA 32:8, no mask).  Few key
+  // tiles per item: the item hand-over weighs more than the 128-key MMAs save, and an inactive handle has half the tiles.
+  if (p.T <= BM || (!forced && p.T < (p.active ? 1024 : 3072))) return false;   // (one query tile: the single-tile kernels)
   if (p.key_mask != nullptr && (size_t)p.B * kbit_words(p.S) * 4 > (size_t)KBITS_MAX) return false;
   return true;
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mimic {
 
@@ -63,12 +64,12 @@ struct Raw8<__nv_bfloat16> {
     stg_hint(p, v, policy);
   }
   __device__ __forceinline__ void unpack(float (&f)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    // one ALU instruction per element (shift / mask); __bfloat1622float2 costs PRMT + shift for the high half
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 t = __bfloat1622float2(h[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
 };
@@ -459,13 +460,16 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) ce_fwd_bwd_kernel
 
 // ---------------------------------------------------------------------------------------------
 // C, register-resident variant (bf16): the logits row never leaves the chip between the statistics and the gradient.
-// A thread-block CLUSTER of CL CTAs x 256 threads owns a row; every thread loads its <= MAXC 16-byte chunks ONCE into
-// registers (raw bf16: 4 registers per chunk), reduces (max, sum) inside its CTA, the CTAs of the cluster exchange their
-// two floats through distributed shared memory (one cluster barrier per row), and the gradient is formed from the same
-// registers and streamed out: dram read == algorithmic (the two-pass kernel re-read 0.36 GB of the 0.47 GB LLaVA logits
-// from HBM: 296 CTAs x 304 KB rows + gradients outgrow L2).  Four CTAs per SM sit in different phases of their rows, so
-// loads, exponentials and stores of neighbouring rows overlap.  CL is the smallest of 1 / 2 / 4 / 8 whose registers hold
-// the row (V <= 20 480 / 40 960 / 81 920 / 163 840); longer rows and fp32 logits take the two-pass kernel above.
+// A thread-block CLUSTER of CL CTAs x 256 threads owns a row; CTA `rank` owns a contiguous run of its 16-byte chunks.
+// While the cluster works on row r, ONE thread per CTA has the CTA's run of the cluster's NEXT row brought into a 40 KB
+// shared-memory stage by a bulk async copy (cp.async.bulk -> mbarrier complete_tx): HBM streams during the exponentials
+// instead of waiting for them (the CTAs of an SM start in lock-step and stay there, so co-residency alone did not overlap
+// the load phase of one row with the arithmetic of another: 0.64 of the HBM peak before the stage).  A row is then
+// stage -> registers (raw bf16: 4 registers per chunk, <= MAXC chunks per thread), (max, sum) reduced inside the CTA, the
+// CTAs of the cluster exchange their two floats through distributed shared memory (one cluster barrier per row), and the
+// gradient is formed from the same registers and streamed out: dram read == algorithmic (the two-pass kernel re-read
+// 0.36 GB of the 0.47 GB LLaVA logits from HBM).  CL is the smallest of 1 / 2 / 4 / 8 whose registers hold the row
+// (V <= 20 480 / 40 960 / 81 920 / 163 840); longer rows and fp32 logits take the two-pass kernel above.
 template <int CL>
 __device__ __forceinline__ void cluster_sync_all() {
   if constexpr (CL > 1) {
@@ -480,17 +484,51 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ float2 dsmem_ld_f2(const float2* local, uint32_t cta) {
-  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
-  return v;
+// global -> this CTA's shared memory, `bytes` (a multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_load_to_stage(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(ptx::smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void stage_wait(uint64_t* bar, uint32_t parity) {
+  while (!ptx::mbar_try_wait(bar, parity)) {
+  }
 }
 
 constexpr int CE_MAXC = 10;
-constexpr int CE_NT = 256;      // threads per CTA: four CTAs per SM (64 registers each) drift apart in phase and overlap their rows
+constexpr int CE_NT = 256;      // threads per CTA: four CTAs per SM (64 registers, 40 KB of stage each)
+constexpr int CE_STAGE_BYTES = CE_MAXC * CE_NT * 16;
+
+// the run of 16-byte chunks CTA `rank` of a CL-cluster owns in a row of `body` chunks: [first, first + count)
+template <int CL>
+__device__ __forceinline__ void cta_run(int body, uint32_t rank, int& first, int& count) {
+  const int per = (body + CL - 1) / CL;
+  first = (int)rank * per;
+  count = body - first;
+  count = count < 0 ? 0 : (count > per ? per : count);
+}
+
+// (max, sum) partials travel between the CTAs of a cluster as asynchronous remote shared-memory stores that complete a
+// transaction count on the RECEIVER's mbarrier (st.async ... mbarrier::complete_tx::bytes): no cluster barrier per row.
+// (barrier.cluster.arrive.release made every row wait until the previous row's gradient stores had drained — `membar`
+// was the second largest stall reason of the kernel — and the partials were then read with 8 remote loads.)
+__device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(ptx::smem_u32(local)), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void st_async_f2(uint32_t remote_dst, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_dst), "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
+// combine (m, s) pairs of a softmax: s is relative to m
+__device__ __forceinline__ void ms_merge(float& M, float& S, float m, float s2) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float Mn = fmaxf(M, m);
+  S = ((M == -INFINITY) ? 0.f : S * fast_ex2((M - Mn) * L2E)) + ((m == -INFINITY) ? 0.f : s2 * fast_ex2((m - Mn) * L2E));
+  M = Mn;
+}
 
 template <int CL>
 __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_kernel(const __nv_bfloat16* __restrict__ logits, int64_t row_stride,
@@ -499,28 +537,67 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
                                                                 float* __restrict__ loss, float* __restrict__ row_loss,
                                                                 unsigned int* __restrict__ counter) {
   using T = __nv_bfloat16;
+  constexpr int NW = CE_NT / 32;
+  extern __shared__ __align__(128) unsigned char ce_stage[];   // CE_STAGE_BYTES: this CTA's run of the next row
   __shared__ float red[32];
   __shared__ float bc[2];
-  __shared__ float2 xchg[2];               // this CTA's (max, sum) of a row, double-buffered by processed-row parity
+  __shared__ float2 wred[2][NW];           // per-warp (max, sum) of a row, double-buffered by processed-row parity
+  __shared__ __align__(8) float2 slots[2][CL];   // (max, sum) of every CTA of the cluster for a row, same double buffer
+  __shared__ uint64_t full_bar;            // the stage holds the row it was armed for
+  __shared__ uint64_t xbar[2];             // slots[par] are complete
   __shared__ bool is_last;
   constexpr float L2E = 1.4426950408889634f;
   const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-  const int gtid = rank * CE_NT + threadIdx.x;
-  constexpr int GT = CL * CE_NT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t stream = l2_stream_policy();
+  if (tid == 0) {
+    ptx::mbar_init(&full_bar, 1);
+    ptx::mbar_init(&xbar[0], 1);
+    ptx::mbar_init(&xbar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  // thread 0: have this CTA's run of row r brought into the stage (rows without a label are never staged)
+  auto stage_row = [&](int r) {
+    if (r >= R || labels[r] < 0) return;
+    const T* x = logits + (int64_t)r * row_stride;
+    const int head = head_elems(x, V);
+    int first, count;
+    cta_run<CL>((V - head) / 8, rank, first, count);
+    if (count > 0) {
+      ptx::mbar_expect_tx(&full_bar, (uint32_t)count * 16u);
+      bulk_load_to_stage(ce_stage, x + head + first * 8, (uint32_t)count * 16u, &full_bar, stream);
+    }
+  };
+  // the <= 7 + 7 elements in front of / behind the 16-byte aligned body (one each for the first threads of CTA 0) and the
+  // logit at the label (thread 64 of CTA 0) are fetched ONE ROW AHEAD, when the stage is armed: nobody waits for them
+  auto edge_index = [&](int head, int tail0) {
+    return rank != 0 ? -1 : (tid < head ? tid : (tid >= 32 && tid < 40 && tail0 + (tid - 32) < V ? tail0 + tid - 32 : -1));
+  };
+  auto edge_fetch = [&](int r) -> float {
+    if (rank != 0 || r >= R) return -INFINITY;
+    const int64_t lab = labels[r];
+    if (lab < 0) return -INFINITY;
+    const T* x = logits + (int64_t)r * row_stride;
+    if (tid == 64) return to_f32(x[lab]);
+    const int head = head_elems(x, V);
+    const int ei = edge_index(head, head + ((V - head) / 8) * 8);
+    return ei >= 0 ? to_f32(x[ei]) : -INFINITY;
+  };
   float cnt = 0.f;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) cnt += labels[i] >= 0 ? 1.f : 0.f;
-  cnt = block_sum(cnt, red);
-  if (threadIdx.x == 0) bc[0] = cnt;
-  __syncthreads();
+  for (int i = tid; i < R; i += blockDim.x) cnt += labels[i] >= 0 ? 1.f : 0.f;
+  cnt = block_sum(cnt, red);                // (its barriers also publish the mbarrier init inside the CTA)
+  if (tid == 0) {
+    bc[0] = cnt;
+    stage_row(cluster_id);
+  }
+  float edge = edge_fetch(cluster_id);
+  cluster_sync_all<CL>();                   // every CTA's exchange barriers exist before anyone sends to them
   const float n_keep = bc[0];
-  __syncthreads();
   const float inv_n = n_keep > 0.f ? 1.f / n_keep : 0.f;
   const float gs = grad_scale * inv_n;
-  uint32_t done = 0;                       // rows this cluster has put through the exchange (slot parity)
-  // (Tried and measured slower, 0.51 vs 0.63 of the HBM peak: prefetching chunk u of the cluster's next row into the
-  // registers of chunk u as soon as its gradient is stored — the interleaved loads and stores of one warp get in each
-  // other's way.  Rows are loaded at the top of their iteration; the two CTAs of an SM provide the overlap.)
+  uint32_t done = 0;                       // rows this cluster has put through the exchange (slot / barrier parity)
+  uint32_t staged = 0;                     // rows this CTA has taken out of its stage (mbarrier phase parity)
   for (int r = cluster_id; r < R; r += n_clusters) {
     const T* x = logits + (int64_t)r * row_stride;
     T* dx = dlogits ? dlogits + (int64_t)r * row_stride : nullptr;
@@ -528,34 +605,52 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
     const int head = head_elems(x, V);
     const int body = (V - head) / 8;
     const int tail0 = head + body * 8;
-    if (label < 0) {                       // (uniform over the cluster: no barrier on this path)
-      if (gtid == 0) row_loss[r] = 0.f;
+    int first, count;
+    cta_run<CL>(body, rank, first, count);
+    if (label < 0) {                       // (uniform over the cluster: no exchange on this path)
+      if (tid == 0) stage_row(r + n_clusters);      // the stage is free: the previous row left it before its arithmetic
+      edge = edge_fetch(r + n_clusters);
+      if (rank == 0 && tid == 0) row_loss[r] = 0.f;
       if (dx) {
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int gtid = rank * CE_NT + tid;
+        constexpr int GT = CL * CE_NT;
         for (int i = gtid; i < head; i += GT) dx[i] = from_f32<T>(0.f);
         for (int c = gtid; c < body; c += GT) Chunk<T>::store(dx + head + c * 8, z);
         for (int i = tail0 + gtid; i < V; i += GT) dx[i] = from_f32<T>(0.f);
       }
       continue;
     }
-    // ---- the row, once: <= MAXC chunks per thread, all loads in flight before the first use ----
+    // ---- the row, once: stage -> registers (<= MAXC chunks per thread), then the stage goes to the next row ----
     Raw8<T> raw[CE_MAXC];
-#pragma unroll
-    for (int u = 0; u < CE_MAXC; ++u) {
-      const int c = gtid + u * GT;
-      if (c < body) raw[u].u = ldg_stream(x + head + c * 8);
+    if (count > 0) {
+      stage_wait(&full_bar, staged & 1);
+      ++staged;
     }
-    // the <= 7 + 7 elements in front of / behind the 16-byte aligned body: one each for the first threads of the cluster
-    const int ei = gtid < head ? gtid : (gtid >= 32 && gtid < 40 && tail0 + (gtid - 32) < V ? tail0 + gtid - 32 : -1);
-    const float ex = ei >= 0 ? to_f32(x[ei]) : -INFINITY;
-    float m = ex;
 #pragma unroll
     for (int u = 0; u < CE_MAXC; ++u) {
-      if (gtid + u * GT < body) {
-        float f[8];
-        raw[u].unpack(f);
-        m = fmaxf(m, fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7]))));
+      const int c = tid + u * CE_NT;
+      if (c < count) raw[u].u = *reinterpret_cast<const uint4*>(ce_stage + (size_t)c * 16);
+    }
+    const int ei = edge_index(head, tail0);
+    const float ex = ei >= 0 ? edge : -INFINITY;
+    const float x_label = edge;            // (thread 64 of CTA 0)
+    __syncthreads();
+    if (tid == 0) stage_row(r + n_clusters);
+    edge = edge_fetch(r + n_clusters);
+    // thread maximum on the packed pairs (VHMNMX.BF16_V2: a quarter of an instruction per element, no unpacking)
+    float m = ex;
+    {
+      __nv_bfloat162 mm = __halves2bfloat162(__ushort_as_bfloat16(0xFF80u), __ushort_as_bfloat16(0xFF80u));   // (-inf, -inf)
+#pragma unroll
+      for (int u = 0; u < CE_MAXC; ++u) {
+        if (tid + u * CE_NT < count) {
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u].u);
+          mm = __hmax2(__hmax2(mm, hh[0]), __hmax2(hh[1], __hmax2(hh[2], hh[3])));
+        }
       }
+      const float2 m2 = __bfloat1622float2(mm);
+      m = fmaxf(m, fmaxf(m2.x, m2.y));
     }
     // e = exp2((x - m_thread) log2e): summed in fp32, then written back over the raw chunk as bf16 pairs — the gradient
     // pass multiplies it by a per-thread factor instead of exponentiating again (ONE MUFU per element, the kernel was
@@ -569,7 +664,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       }
 #pragma unroll
       for (int u = 0; u < CE_MAXC; ++u) {
-        if (gtid + u * GT < body) {
+        if (tid + u * CE_NT < count) {
           float f[8];
           raw[u].unpack(f);
 #pragma unroll
@@ -583,55 +678,79 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
         }
       }
     }
-    // ---- CTA (max, sum), then the cluster's ----
-    float gm = m;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
-    __syncthreads();
-    gm = red[0];
-#pragma unroll
-    for (int wi = 1; wi < CE_NT / 32; ++wi) gm = fmaxf(gm, red[wi]);
-    float ss = (m == -INFINITY) ? 0.f : s * fast_ex2((m - gm) * L2E);
-    ss = block_sum(ss, red);
+    // ---- warp (max, sum) -> shared; ONE block barrier; every thread merges the 8 warps; the cluster's by st.async ----
     const int par = done & 1;
-    if (threadIdx.x == 0) xchg[par] = make_float2(gm, ss);
-    cluster_sync_all<CL>();
+    {
+      float wm = m;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      float ws = (m == -INFINITY) ? 0.f : s * fast_ex2((m - wm) * L2E);
+      ws = warp_sum(ws);
+      if (lane == 0) wred[par][warp] = make_float2(wm, ws);
+    }
+    __syncthreads();
     float M = -INFINITY, Ssum = 0.f;
 #pragma unroll
-    for (int c = 0; c < CL; ++c) {
-      const float2 v = CL > 1 ? dsmem_ld_f2(&xchg[par], (uint32_t)c) : xchg[par];
-      const float Mn = fmaxf(M, v.x);
-      Ssum = Ssum * ((M == -INFINITY) ? 0.f : fast_ex2((M - Mn) * L2E)) + v.y * fast_ex2((v.x - Mn) * L2E);
-      M = Mn;
+    for (int wi = 0; wi < NW; ++wi) {
+      const float2 v = wred[par][wi];
+      ms_merge(M, Ssum, v.x, v.y);
+    }
+    if constexpr (CL > 1) {
+      if (tid == 0) ptx::mbar_expect_tx(&xbar[par], CL * 8u);
+      if (tid < CL) st_async_f2(map_to_cta(&slots[par][rank], (uint32_t)tid), M, Ssum, map_to_cta(&xbar[par], (uint32_t)tid));
+      stage_wait(&xbar[par], (done >> 1) & 1);
+      M = -INFINITY;
+      Ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CL; ++c) {
+        const float2 v = slots[par][c];
+        ms_merge(M, Ssum, v.x, v.y);
+      }
     }
     ++done;
     const float lse = M + __logf(Ssum);
-    if (gtid == 0) row_loss[r] = lse - to_f32(x[label]);
-    // ---- gradient from the same registers: p = e * exp2((m_thread - lse) log2e), one multiply per element ----
+    if (rank == 0 && tid == 64) row_loss[r] = lse - x_label;
+    // ---- gradient from the same registers: p = e * exp2((m_thread - lse) log2e) on the packed pairs ----
+    // fac = fh + fl (two bf16 terms: fac to 2^-17), g = e * fh + e * fl with HFMA2.BF16 — one rounding to bf16 as before,
+    // a quarter of the instructions of unpack / FMUL / pack (the kernel is issue-bound: ~1950 instructions per thread and
+    // row before this, 0.62 of the HBM peak)
     const float fac = (m == -INFINITY) ? 0.f : gs * fast_ex2((m - lse) * L2E);
-    if (dx && ei >= 0) dx[ei] = from_f32<T>(ee * fac - (ei == (int)label ? gs : 0.f));
-    const int lab_c = ((int)label - head) >> 3;             // chunk that holds the label (only it pays the compare)
+    if (dx) {
+      if (ei >= 0) dx[ei] = from_f32<T>(ee * fac - (ei == (int)label ? gs : 0.f));
+      const __nv_bfloat16 fh = __float2bfloat16_rn(fac);
+      const __nv_bfloat16 fl = __float2bfloat16_rn(fac - __bfloat162float(fh));
+      const __nv_bfloat162 fh2 = __halves2bfloat162(fh, fh), fl2 = __halves2bfloat162(fl, fl);
+      const int lab_e = (int)label - head - first * 8;      // position of the label inside this CTA's run (may be outside it)
+      const int lab_c = lab_e >= 0 ? (lab_e >> 3) : -1;     // the chunk of the run that holds it: only that one is patched
+      T* dxp = dx + head + (size_t)(first + tid) * 8;
 #pragma unroll
-    for (int u = 0; u < CE_MAXC; ++u) {
-      const int c = gtid + u * GT;
-      if (dx && c < body) {
-        float f[8];
-        raw[u].unpack(f);
+      for (int u = 0; u < CE_MAXC; ++u) {
+        const int c = tid + u * CE_NT;
+        if (c < count) {
+          uint4 g;
+          __nv_bfloat162* gg = reinterpret_cast<__nv_bfloat162*>(&g);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u].u);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] *= fac;
-        if (c == lab_c && (int)label >= head) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (head + c * 8 + e == (int)label) f[e] -= gs;
+          for (int e = 0; e < 4; ++e) gg[e] = __hfma2(hh[e], fh2, __hmul2(hh[e], fl2));
+          if (c == lab_c) {                                 // p - 1 at the label, in fp32 like every other element was before
+            const int k = lab_e & 7;
+            const uint32_t w = k < 2 ? raw[u].u.x : (k < 4 ? raw[u].u.y : (k < 6 ? raw[u].u.z : raw[u].u.w));
+            const float e_lab = __uint_as_float((k & 1) ? (w & 0xffff0000u) : (w << 16));
+            const uint32_t pv = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e_lab * fac - gs));
+            const uint32_t keep = (k & 1) ? 0x0000ffffu : 0xffff0000u, val = (k & 1) ? (pv << 16) : pv;
+            const int ws = k >> 1;                          // (selects, not a reference: g stays in registers)
+            g.x = ws == 0 ? ((g.x & keep) | val) : g.x;
+            g.y = ws == 1 ? ((g.y & keep) | val) : g.y;
+            g.z = ws == 2 ? ((g.z & keep) | val) : g.z;
+            g.w = ws == 3 ? ((g.w & keep) | val) : g.w;
+          }
+          stg_stream(dxp + (size_t)u * CE_NT * 8, g);
         }
-        Chunk<T>::store(dx + head + c * 8, f);
       }
     }
   }
-  cluster_sync_all<CL>();                   // no CTA leaves while a neighbour may still read its exchange slot
-  if (threadIdx.x == 0) {
+  cluster_sync_all<CL>();                   // no CTA leaves while a neighbour may still send to its slots
+  if (tid == 0) {
     __threadfence();
     is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
@@ -639,9 +758,9 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
   if (is_last) {
     __threadfence();
     float tot = 0.f;
-    for (int i = threadIdx.x; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
+    for (int i = tid; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
     tot = block_sum(tot, red);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       loss[0] = tot * inv_n;
       n_kept[0] = (int32_t)(n_keep + 0.5f);
       *counter = 0u;
@@ -655,7 +774,7 @@ static int launch_ce_reg(const __nv_bfloat16* logits, int64_t row_stride, const 
                          cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(CE_NT);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = CE_STAGE_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -668,6 +787,8 @@ static int launch_ce_reg(const __nv_bfloat16* logits, int64_t row_stride, const 
   // start its static share of the rows when the others are done — measured: 74 launched, 71 resident, SMs 33 % idle)
   static int max_clusters = 0;
   if (max_clusters == 0) {
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(ce_fwd_bwd_reg_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
     cfg.gridDim = dim3(CL * num_sms() * 4);
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, ce_fwd_bwd_reg_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = num_sms() * (65536 / (CE_NT * 64)) / CL - 4;
@@ -985,13 +1106,8 @@ __device__ __forceinline__ uint4 ldg_window_part(const uint4* p, uint64_t policy
                : "l"(p), "l"(policy));
   return r;
 }
-__device__ __forceinline__ uint4 load16_window(const void* p, uint64_t policy) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint4* base = reinterpret_cast<const uint4*>(a & ~uintptr_t(15));
-  const unsigned o = (unsigned)(a & 15);
-  const uint4 lo = ldg_window_part(base, policy);
-  if (o == 0) return lo;
-  const uint4 hi = ldg_window_part(base + 1, policy);
+// bytes [o, o + 16) of the 32 bytes (lo, hi), 0 < o < 16
+__device__ __forceinline__ uint4 window_combine(const uint4& lo, const uint4& hi, unsigned o) {
   const unsigned long long q0 = ((unsigned long long)lo.y << 32) | lo.x, q1 = ((unsigned long long)lo.w << 32) | lo.z;
   const unsigned long long q2 = ((unsigned long long)hi.y << 32) | hi.x, q3 = ((unsigned long long)hi.w << 32) | hi.z;
   const unsigned long long x0 = o < 8 ? q0 : q1, x1 = o < 8 ? q1 : q2, x2 = o < 8 ? q2 : q3;
@@ -999,6 +1115,14 @@ __device__ __forceinline__ uint4 load16_window(const void* p, uint64_t policy) {
   const unsigned long long r0 = sh ? (x0 >> sh) | (x1 << (64 - sh)) : x0;
   const unsigned long long r1 = sh ? (x1 >> sh) | (x2 << (64 - sh)) : x1;
   return make_uint4((unsigned)r0, (unsigned)(r0 >> 32), (unsigned)r1, (unsigned)(r1 >> 32));
+}
+__device__ __forceinline__ uint4 load16_window(const void* p, uint64_t policy) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint4* base = reinterpret_cast<const uint4*>(a & ~uintptr_t(15));
+  const unsigned o = (unsigned)(a & 15);
+  const uint4 lo = ldg_window_part(base, policy);
+  if (o == 0) return lo;
+  return window_combine(lo, ldg_window_part(base + 1, policy), o);
 }
 __device__ __forceinline__ void load8_window(const __nv_bfloat16* p, float (&f)[8], uint64_t policy) {
   const uint4 u = load16_window(p, policy);
@@ -1179,6 +1303,321 @@ __global__ void __launch_bounds__(512, sizeof(T) == 2 ? 2 : 1) kl_fwd_bwd_kernel
       *counter = 0u;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KL, register-resident variant (bf16) — the construction of ce_fwd_bwd_reg_kernel with two rows per item: a cluster of
+// CL CTAs x 256 threads owns a pair (z row, matching y row); each CTA's contiguous run of the NEXT pair is brought into two
+// 40 KB shared-memory stages by bulk async copies while the current pair is being worked on.  z chunks are 16-byte
+// aligned; the y row starts at an unrelated alignment (V is odd for the real vocabularies), so its stage holds the aligned
+// superset of the run and a thread assembles its chunk from two neighbouring 16-byte vectors (byte funnel shift).  Stage ->
+// registers (raw bf16, 2 x 4 registers per chunk, <= KL_MAXC chunks per thread, 128 registers per thread, two CTAs per
+// SM), (m_z, s_z, m_y, s_y, A) reduced inside the CTA, five floats exchanged through distributed shared memory, gradient
+// from the same registers.  Both exponentials are evaluated again in the gradient pass (softmax(z) - softmax(y) tends to
+// zero as training converges: a bf16-rounded e would put a 2^-9 relative error of EACH term into the difference), so the
+// kernel pays 4 MUFU per element pair: at 16 / clk / SM that alone is 6.7 TB/s of algorithmic bytes, i.e. the MUFU pipe
+// and HBM are co-limiting.  dram read == algorithmic: 2 rows in, 1 row out.  CL = smallest of 1 / 2 / 4 / 8 with V <= CL * 20 480.
+constexpr int KL_MAXC = 10;
+constexpr int KL_NT = 256;
+constexpr int KL_STAGE_Z = KL_MAXC * KL_NT * 16, KL_STAGE_Y = KL_STAGE_Z + 16;
+
+struct __align__(16) KlPart {
+  float mz, sz, my, sy, ay, pad0, pad1, pad2;
+};
+__device__ __forceinline__ void st_async_f4(uint32_t remote_dst, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_dst), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t remote_dst, float a, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(remote_dst), "f"(a), "r"(remote_bar)
+               : "memory");
+}
+// combine the partials of a row pair: s_z relative to m_z; s_y and A relative to m_y
+__device__ __forceinline__ void kl_merge(KlPart& t, float mz, float sz, float my, float sy, float ay) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float Mz = fmaxf(t.mz, mz), My = fmaxf(t.my, my);
+  const float oz = (t.mz == -INFINITY) ? 0.f : fast_ex2((t.mz - Mz) * L2E), nz = (mz == -INFINITY) ? 0.f : fast_ex2((mz - Mz) * L2E);
+  const float oy = (t.my == -INFINITY) ? 0.f : fast_ex2((t.my - My) * L2E), ny = (my == -INFINITY) ? 0.f : fast_ex2((my - My) * L2E);
+  t.sz = t.sz * oz + sz * nz;
+  t.sy = t.sy * oy + sy * ny;
+  t.ay = t.ay * oy + ay * ny;
+  t.mz = Mz;
+  t.my = My;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(KL_NT, 2) kl_fwd_bwd_reg_kernel(const __nv_bfloat16* __restrict__ zl, int64_t z_stride,
+                                                                  const __nv_bfloat16* __restrict__ yl, int64_t y_stride,
+                                                                  const int32_t* __restrict__ y_row, __nv_bfloat16* dz,
+                                                                  float grad_scale, int R, int V, int32_t* __restrict__ n_rows,
+                                                                  float* __restrict__ loss, float* __restrict__ row_loss,
+                                                                  unsigned int* __restrict__ counter) {
+  using T = __nv_bfloat16;
+  constexpr int NW = KL_NT / 32;
+  extern __shared__ __align__(128) unsigned char kl_stage[];   // [KL_STAGE_Z] z run | [KL_STAGE_Y] aligned superset of the y run
+  unsigned char* stage_z = kl_stage;
+  unsigned char* stage_y = kl_stage + KL_STAGE_Z;
+  __shared__ float red[32];
+  __shared__ float bc[1];
+  __shared__ KlPart wred[2][NW];           // per-warp partials of a row pair, double-buffered by processed-row parity
+  __shared__ KlPart slots[2][CL];          // partials of every CTA of the cluster, same double buffer (filled by st.async)
+  __shared__ uint64_t full_bar;            // both stages hold the pair they were armed for
+  __shared__ uint64_t xbar[2];             // slots[par] are complete
+  __shared__ bool is_last;
+  constexpr float L2E = 1.4426950408889634f;
+  const uint64_t stream = l2_stream_policy();
+  const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    ptx::mbar_init(&full_bar, 1);
+    ptx::mbar_init(&xbar[0], 1);
+    ptx::mbar_init(&xbar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  // thread 0: have this CTA's run of pair r brought into the stages (unselected rows are never staged)
+  auto stage_pair = [&](int r) {
+    if (r >= R) return;
+    const int yr = y_row[r];
+    if (yr < 0) return;
+    const T* z = zl + (int64_t)r * z_stride;
+    const T* y = yl + (int64_t)yr * y_stride;
+    const int head = head_elems(z, V);
+    int first, count;
+    cta_run<CL>((V - head) / 8, rank, first, count);
+    if (count > 0) {
+      const uintptr_t ya = reinterpret_cast<uintptr_t>(y + head + first * 8);
+      const uint32_t yo = (uint32_t)(ya & 15), zb = (uint32_t)count * 16u, yb = zb + (yo ? 16u : 0u);
+      ptx::mbar_expect_tx(&full_bar, zb + yb);
+      bulk_load_to_stage(stage_z, z + head + first * 8, zb, &full_bar, stream);
+      bulk_load_to_stage(stage_y, reinterpret_cast<const void*>(ya - yo), yb, &full_bar, stream);
+    }
+  };
+  // the <= 7 + 7 element pairs around the aligned body (one each for the first threads of CTA 0), fetched one pair ahead
+  auto edge_index = [&](int head, int tail0) {
+    return rank != 0 ? -1 : (tid < head ? tid : (tid >= 32 && tid < 40 && tail0 + (tid - 32) < V ? tail0 + tid - 32 : -1));
+  };
+  auto edge_fetch = [&](int r, float& ez, float& ey) {
+    ez = ey = -INFINITY;
+    if (rank != 0 || r >= R) return;
+    const int yr = y_row[r];
+    if (yr < 0) return;
+    const T* z = zl + (int64_t)r * z_stride;
+    const int head = head_elems(z, V);
+    const int ei = edge_index(head, head + ((V - head) / 8) * 8);
+    if (ei >= 0) {
+      ez = to_f32(z[ei]);
+      ey = to_f32(yl[(int64_t)yr * y_stride + ei]);
+    }
+  };
+  float cnt = 0.f;
+  for (int i = tid; i < R; i += blockDim.x) cnt += y_row[i] >= 0 ? 1.f : 0.f;
+  cnt = block_sum(cnt, red);                // (its barriers also publish the mbarrier init inside the CTA)
+  if (tid == 0) {
+    bc[0] = cnt;
+    stage_pair(cluster_id);
+  }
+  float edge_z, edge_y;
+  edge_fetch(cluster_id, edge_z, edge_y);
+  cluster_sync_all<CL>();                   // every CTA's exchange barriers exist before anyone sends to them
+  const float n_sel = bc[0];
+  const float inv_n = n_sel > 0.f ? 1.f / n_sel : 0.f;
+  const float gs = grad_scale * inv_n;
+  uint32_t done = 0, staged = 0;
+  for (int r = cluster_id; r < R; r += n_clusters) {
+    const T* z = zl + (int64_t)r * z_stride;
+    T* d = dz ? dz + (int64_t)r * z_stride : nullptr;
+    const int yr = y_row[r];
+    const int head = head_elems(z, V);           // chunks are aligned for z (and dz); y is read through windows
+    const int body = (V - head) / 8;
+    const int tail0 = head + body * 8;
+    int first, count;
+    cta_run<CL>(body, rank, first, count);
+    if (yr < 0) {                                // (uniform over the cluster: no exchange on this path)
+      if (tid == 0) stage_pair(r + n_clusters);  // the stages are free: the previous pair left them before its arithmetic
+      edge_fetch(r + n_clusters, edge_z, edge_y);
+      if (rank == 0 && tid == 0) row_loss[r] = 0.f;
+      if (d) {
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int gtid = rank * KL_NT + tid;
+        constexpr int GT = CL * KL_NT;
+        for (int i = gtid; i < head; i += GT) d[i] = from_f32<T>(0.f);
+        for (int c = gtid; c < body; c += GT) Chunk<T>::store(d + head + c * 8, zero);
+        for (int i = tail0 + gtid; i < V; i += GT) d[i] = from_f32<T>(0.f);
+      }
+      continue;
+    }
+    const unsigned yo = (unsigned)(reinterpret_cast<uintptr_t>(yl + (int64_t)yr * y_stride + head + first * 8) & 15);
+    // ---- both rows, once: stages -> registers, then the stages go to the next pair ----
+    Raw8<T> rz[KL_MAXC], ry[KL_MAXC];
+    if (count > 0) {
+      stage_wait(&full_bar, staged & 1);
+      ++staged;
+    }
+#pragma unroll
+    for (int u = 0; u < KL_MAXC; ++u) {
+      const int c = tid + u * KL_NT;
+      if (c < count) {
+        rz[u].u = *reinterpret_cast<const uint4*>(stage_z + (size_t)c * 16);
+        const uint4 lo = *reinterpret_cast<const uint4*>(stage_y + (size_t)c * 16);
+        ry[u].u = yo ? window_combine(lo, *reinterpret_cast<const uint4*>(stage_y + (size_t)c * 16 + 16), yo) : lo;
+      }
+    }
+    const int ei = edge_index(head, tail0);
+    const float ez = ei >= 0 ? edge_z : -INFINITY, ey = ei >= 0 ? edge_y : -INFINITY;
+    __syncthreads();
+    if (tid == 0) stage_pair(r + n_clusters);
+    edge_fetch(r + n_clusters, edge_z, edge_y);
+    float mz = ez, my = ey;
+    {
+      const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16(0xFF80u), __ushort_as_bfloat16(0xFF80u));
+      __nv_bfloat162 pz = ninf, py = ninf;         // thread maxima on the packed pairs (no unpacking)
+#pragma unroll
+      for (int u = 0; u < KL_MAXC; ++u) {
+        if (tid + u * KL_NT < count) {
+          const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&rz[u].u);
+          const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ry[u].u);
+          pz = __hmax2(__hmax2(pz, hz[0]), __hmax2(hz[1], __hmax2(hz[2], hz[3])));
+          py = __hmax2(__hmax2(py, hy[0]), __hmax2(hy[1], __hmax2(hy[2], hy[3])));
+        }
+      }
+      const float2 a = __bfloat1622float2(pz), b = __bfloat1622float2(py);
+      mz = fmaxf(mz, fmaxf(a.x, a.y));
+      my = fmaxf(my, fmaxf(b.x, b.y));
+    }
+    float sz = 0.f, sy = 0.f, ay = 0.f;
+    {
+      const float nmz = (mz == -INFINITY) ? 0.f : -mz * L2E, nmy = (my == -INFINITY) ? 0.f : -my * L2E;
+      if (ei >= 0) {
+        sz += fast_ex2(fmaf(ez, L2E, nmz));
+        const float e = fast_ex2(fmaf(ey, L2E, nmy));
+        sy += e;
+        ay = fmaf(e, ey - ez, ay);
+      }
+#pragma unroll
+      for (int u = 0; u < KL_MAXC; ++u) {
+        if (tid + u * KL_NT < count) {
+          float fz[8], fy[8];
+          rz[u].unpack(fz);
+          ry[u].unpack(fy);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sz += fast_ex2(fmaf(fz[e], L2E, nmz));
+            const float t = fast_ex2(fmaf(fy[e], L2E, nmy));
+            sy += t;
+            ay = fmaf(t, fy[e] - fz[e], ay);
+          }
+        }
+      }
+    }
+    // ---- warp partials -> shared; ONE block barrier; every thread merges the 8 warps; the cluster's by st.async ----
+    const int par = done & 1;
+    {
+      float wz = mz, wy = my;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wz = fmaxf(wz, __shfl_xor_sync(0xffffffffu, wz, o));
+        wy = fmaxf(wy, __shfl_xor_sync(0xffffffffu, wy, o));
+      }
+      const float fzs = (mz == -INFINITY) ? 0.f : fast_ex2((mz - wz) * L2E), fys = (my == -INFINITY) ? 0.f : fast_ex2((my - wy) * L2E);
+      const float a = warp_sum(sz * fzs), b = warp_sum(sy * fys), c = warp_sum(ay * fys);
+      if (lane == 0) wred[par][warp] = KlPart{wz, a, wy, b, c, 0.f, 0.f, 0.f};
+    }
+    __syncthreads();
+    KlPart tot = {-INFINITY, 0.f, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int wi = 0; wi < NW; ++wi) {
+      const float4 v = *reinterpret_cast<const float4*>(&wred[par][wi]);
+      kl_merge(tot, v.x, v.y, v.z, v.w, wred[par][wi].ay);
+    }
+    if constexpr (CL > 1) {
+      if (tid == 0) ptx::mbar_expect_tx(&xbar[par], CL * 20u);
+      if (tid < CL) {
+        const uint32_t dst = map_to_cta(&slots[par][rank], (uint32_t)tid), bar = map_to_cta(&xbar[par], (uint32_t)tid);
+        st_async_f4(dst, tot.mz, tot.sz, tot.my, tot.sy, bar);
+        st_async_f1(dst + 16, tot.ay, bar);
+      }
+      stage_wait(&xbar[par], (done >> 1) & 1);
+      tot = KlPart{-INFINITY, 0.f, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < CL; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(&slots[par][c]);
+        kl_merge(tot, v.x, v.y, v.z, v.w, slots[par][c].ay);
+      }
+    }
+    ++done;
+    const float lse_z = tot.mz + __logf(tot.sz), lse_y = tot.my + __logf(tot.sy);
+    if (rank == 0 && tid == 0) row_loss[r] = tot.ay / tot.sy - lse_y + lse_z;
+    // ---- gradient from the same registers ----
+    if (d) {
+      const float nlz2 = -lse_z * L2E, nly2 = -lse_y * L2E;
+      if (ei >= 0) d[ei] = from_f32<T>(gs * (fast_ex2(fmaf(ez, L2E, nlz2)) - fast_ex2(fmaf(ey, L2E, nly2))));
+      T* dp = d + head + (size_t)(first + tid) * 8;
+#pragma unroll
+      for (int u = 0; u < KL_MAXC; ++u) {
+        const int c = tid + u * KL_NT;
+        if (c < count) {
+          float fz[8], fy[8];
+          rz[u].unpack(fz);
+          ry[u].unpack(fy);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fz[e] = gs * (fast_ex2(fmaf(fz[e], L2E, nlz2)) - fast_ex2(fmaf(fy[e], L2E, nly2)));
+          Chunk<T>::store(dp + (size_t)u * KL_NT * 8, fz);
+        }
+      }
+    }
+  }
+  cluster_sync_all<CL>();                   // no CTA leaves while a neighbour may still send to its slots
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = tid; i < R; i += blockDim.x) tot += __ldcg(row_loss + i);
+    tot = block_sum(tot, red);
+    if (tid == 0) {
+      loss[0] = tot * inv_n;
+      n_rows[0] = (int32_t)(n_sel + 0.5f);
+      *counter = 0u;
+    }
+  }
+}
+
+template <int CL>
+static int launch_kl_reg(const __nv_bfloat16* z, int64_t z_stride, const __nv_bfloat16* y, int64_t y_stride, const int32_t* y_row,
+                         __nv_bfloat16* dz, float grad_scale, int R, int V, int32_t* n_rows, float* loss, float* row_loss,
+                         unsigned int* counter, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(KL_NT);
+  cfg.dynamicSmemBytes = KL_STAGE_Z + KL_STAGE_Y;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;              // persistent clusters: as many as the device co-schedules (see launch_ce_reg)
+  if (max_clusters == 0) {
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(kl_fwd_bwd_reg_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, KL_STAGE_Z + KL_STAGE_Y));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(kl_fwd_bwd_reg_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+    cfg.gridDim = dim3(CL * num_sms() * 2);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kl_fwd_bwd_reg_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = num_sms() * 2 / CL - 4;
+    max_clusters = n > 0 ? n : 1;
+  }
+  const int n_clusters = max_clusters < R ? max_clusters : R;
+  cfg.gridDim = dim3(n_clusters * CL);
+  MIMIC_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fwd_bwd_reg_kernel<CL>, z, z_stride, y, y_stride, y_row, dz, grad_scale, R, V, n_rows,
+                                   loss, row_loss, counter));
+  return MIMIC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1461,6 +1900,20 @@ extern "C" int mimic_kl_fwd_bwd(const void* z, int64_t z_row_stride, const void*
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
   float* row_loss = static_cast<float*>(workspace) + 4;
   const int grid = R < num_sms() * 4 ? R : num_sms() * 4;
+  static const bool two_pass = getenv("MIMIC_KL_TWO_PASS") != nullptr;     // (A/B switch, read once)
+  constexpr int cap1 = KL_NT * KL_MAXC * 8;
+  if (dtype == MIMIC_BF16 && V <= 8 * cap1 && !two_pass) {
+    const __nv_bfloat16 *zz = (const __nv_bfloat16*)z, *yy = (const __nv_bfloat16*)y;
+    __nv_bfloat16* dd = (__nv_bfloat16*)dz;
+    int rc;
+    if (V <= cap1) rc = launch_kl_reg<1>(zz, z_row_stride, yy, y_row_stride, y_row, dd, grad_scale, R, V, n_rows, loss, row_loss, counter, st);
+    else if (V <= 2 * cap1) rc = launch_kl_reg<2>(zz, z_row_stride, yy, y_row_stride, y_row, dd, grad_scale, R, V, n_rows, loss, row_loss, counter, st);
+    else if (V <= 4 * cap1) rc = launch_kl_reg<4>(zz, z_row_stride, yy, y_row_stride, y_row, dd, grad_scale, R, V, n_rows, loss, row_loss, counter, st);
+    else rc = launch_kl_reg<8>(zz, z_row_stride, yy, y_row_stride, y_row, dd, grad_scale, R, V, n_rows, loss, row_loss, counter, st);
+    if (rc != MIMIC_OK) return rc;
+    MIMIC_LAUNCH_OK("kl_fwd_bwd_reg_kernel");
+    return MIMIC_OK;
+  }
   if (dtype == MIMIC_BF16)
     kl_fwd_bwd_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>((const __nv_bfloat16*)z, z_row_stride, (const __nv_bfloat16*)y,
                                                            y_row_stride, y_row, (__nv_bfloat16*)dz, grad_scale, R, V, n_rows,

@@ -17,7 +17,7 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _step(preset, dtype, oracle_attention, lora=False, strategies=None, **cfg_over):
+def _step(preset, dtype, oracle_attention, lora=False, strategies=None, upcast=False, **cfg_over):
     from oracle import shifted_attention as OA
     from mimic_b200 import AttnApproximator, HookedModel, ShiftModel, Strategy
     from mimic_b200.backbone import build_synthetic, synthetic_batch, synthetic_processor
@@ -32,6 +32,8 @@ def _step(preset, dtype, oracle_attention, lora=False, strategies=None, **cfg_ov
             for n, p in model.named_parameters():
                 if ".lora_B." in n:
                     p.normal_(0.0, 0.1, generator=g)            # B = 0 would hide the adapter path
+    if upcast:                                                  # the same (rounded) weights, fp32 arithmetic: the "truth" arm
+        model = model.float()
     lmm = HookedModel(model, name, processor=synthetic_processor())
     enc = AttnApproximator(lmm, *(strategies or MIMIC)).cuda()
     g = torch.Generator().manual_seed(11)
@@ -55,6 +57,8 @@ def _step(preset, dtype, oracle_attention, lora=False, strategies=None, **cfg_ov
     if model.config.cross_layer_interval > 0:
         gi = torch.Generator().manual_seed(7)
         img = torch.randn(2, 4 * 8, model.config.vision_embed_dim, generator=gi).to("cuda", dtype)
+        if upcast:
+            img = img.float()
         inputs["image_hidden_states"] = img                     # 3 context images + the query image
         q_inputs["image_hidden_states"] = img[:, -8:]           # the query image only
     loss = sm.forward_inputs(inputs, q_inputs)

@@ -160,7 +160,7 @@ def test_align_cos_and_kl_reference_golden():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (3, 151655), (300, 513)])
+@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (3, 60001), (3, 151655), (300, 513)])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_kl_matches_oracle(dtype, R, V, inplace):
     """Strategy.LOGITS_KL_DIV kernel vs F.kl_div (src/shift_model.py:181-191), odd vocabularies, unselected rows."""
@@ -184,7 +184,7 @@ def test_kl_matches_oracle(dtype, R, V, inplace):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (5, 151655), (300, 513)])
+@pytest.mark.parametrize("R,V", [(7, 50), (37, 32003), (3, 60001), (5, 151655), (300, 513)])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_ce_matches_oracle(dtype, R, V, inplace):
     from mimic_b200 import ops
