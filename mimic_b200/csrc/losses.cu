@@ -496,8 +496,6 @@ __device__ __forceinline__ void stage_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int CE_MAXC = 10;
-constexpr int CE_NT = 256;      // threads per CTA: four CTAs per SM (64 registers, 40 KB of stage each)
-constexpr int CE_STAGE_BYTES = CE_MAXC * CE_NT * 16;
 
 // the run of 16-byte chunks CTA `rank` of a CL-cluster owns in a row of `body` chunks: [first, first + count)
 template <int CL>
@@ -522,23 +520,29 @@ __device__ __forceinline__ void st_async_f2(uint32_t remote_dst, float a, float 
                ::"r"(remote_dst), "f"(a), "f"(b), "r"(remote_bar)
                : "memory");
 }
-// combine (m, s) pairs of a softmax: s is relative to m
-__device__ __forceinline__ void ms_merge(float& M, float& S, float m, float s2) {
+// combine N <= 32 (max, sum) pairs of a softmax (sum relative to its max) held in shared memory: lane i takes pair i, the
+// maximum and then the rescaled sum go through warp shuffles — every warp does it redundantly, no registers for the N
+// pairs, no data-dependent selects; (-inf, 0) entries drop out (2^-inf = 0)
+template <int N>
+__device__ __forceinline__ void ms_combine(const float2* v, int lane, float& M, float& S) {
   constexpr float L2E = 1.4426950408889634f;
-  const float Mn = fmaxf(M, m);
-  S = ((M == -INFINITY) ? 0.f : S * fast_ex2((M - Mn) * L2E)) + ((m == -INFINITY) ? 0.f : s2 * fast_ex2((m - Mn) * L2E));
-  M = Mn;
+  const float2 t = lane < N ? v[lane] : make_float2(-INFINITY, 0.f);
+  M = t.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  const float nM = (M == -INFINITY) ? 0.f : -M * L2E;
+  S = warp_sum(t.y * fast_ex2(fmaf(t.x, L2E, nM)));
 }
 
-template <int CL>
-__global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_kernel(const __nv_bfloat16* __restrict__ logits, int64_t row_stride,
+template <int CL, int NT>
+__global__ void __launch_bounds__(NT, 65536 / (NT * 64)) ce_fwd_bwd_reg_kernel(const __nv_bfloat16* __restrict__ logits, int64_t row_stride,
                                                                 const int64_t* __restrict__ labels, __nv_bfloat16* dlogits,
                                                                 float grad_scale, int R, int V, int32_t* __restrict__ n_kept,
                                                                 float* __restrict__ loss, float* __restrict__ row_loss,
                                                                 unsigned int* __restrict__ counter) {
   using T = __nv_bfloat16;
-  constexpr int NW = CE_NT / 32;
-  extern __shared__ __align__(128) unsigned char ce_stage[];   // CE_STAGE_BYTES: this CTA's run of the next row
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char ce_stage[];   // CE_MAXC * NT * 16 bytes: this CTA's run of the next row
   __shared__ float red[32];
   __shared__ float bc[2];
   __shared__ float2 wred[2][NW];           // per-warp (max, sum) of a row, double-buffered by processed-row parity
@@ -613,8 +617,8 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       if (rank == 0 && tid == 0) row_loss[r] = 0.f;
       if (dx) {
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int gtid = rank * CE_NT + tid;
-        constexpr int GT = CL * CE_NT;
+        const int gtid = rank * NT + tid;
+        constexpr int GT = CL * NT;
         for (int i = gtid; i < head; i += GT) dx[i] = from_f32<T>(0.f);
         for (int c = gtid; c < body; c += GT) Chunk<T>::store(dx + head + c * 8, z);
         for (int i = tail0 + gtid; i < V; i += GT) dx[i] = from_f32<T>(0.f);
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
     }
 #pragma unroll
     for (int u = 0; u < CE_MAXC; ++u) {
-      const int c = tid + u * CE_NT;
+      const int c = tid + u * NT;
       if (c < count) raw[u].u = *reinterpret_cast<const uint4*>(ce_stage + (size_t)c * 16);
     }
     const int ei = edge_index(head, tail0);
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       __nv_bfloat162 mm = __halves2bfloat162(__ushort_as_bfloat16(0xFF80u), __ushort_as_bfloat16(0xFF80u));   // (-inf, -inf)
 #pragma unroll
       for (int u = 0; u < CE_MAXC; ++u) {
-        if (tid + u * CE_NT < count) {
+        if (tid + u * NT < count) {
           const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u].u);
           mm = __hmax2(__hmax2(mm, hh[0]), __hmax2(hh[1], __hmax2(hh[2], hh[3])));
         }
@@ -664,7 +668,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       }
 #pragma unroll
       for (int u = 0; u < CE_MAXC; ++u) {
-        if (tid + u * CE_NT < count) {
+        if (tid + u * NT < count) {
           float f[8];
           raw[u].unpack(f);
 #pragma unroll
@@ -689,23 +693,13 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       if (lane == 0) wred[par][warp] = make_float2(wm, ws);
     }
     __syncthreads();
-    float M = -INFINITY, Ssum = 0.f;
-#pragma unroll
-    for (int wi = 0; wi < NW; ++wi) {
-      const float2 v = wred[par][wi];
-      ms_merge(M, Ssum, v.x, v.y);
-    }
+    float M, Ssum;
+    ms_combine<NW>(wred[par], lane, M, Ssum);
     if constexpr (CL > 1) {
       if (tid == 0) ptx::mbar_expect_tx(&xbar[par], CL * 8u);
       if (tid < CL) st_async_f2(map_to_cta(&slots[par][rank], (uint32_t)tid), M, Ssum, map_to_cta(&xbar[par], (uint32_t)tid));
       stage_wait(&xbar[par], (done >> 1) & 1);
-      M = -INFINITY;
-      Ssum = 0.f;
-#pragma unroll
-      for (int c = 0; c < CL; ++c) {
-        const float2 v = slots[par][c];
-        ms_merge(M, Ssum, v.x, v.y);
-      }
+      ms_combine<CL>(slots[par], lane, M, Ssum);
     }
     ++done;
     const float lse = M + __logf(Ssum);
@@ -725,7 +719,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
       T* dxp = dx + head + (size_t)(first + tid) * 8;
 #pragma unroll
       for (int u = 0; u < CE_MAXC; ++u) {
-        const int c = tid + u * CE_NT;
+        const int c = tid + u * NT;
         if (c < count) {
           uint4 g;
           __nv_bfloat162* gg = reinterpret_cast<__nv_bfloat162*>(&g);
@@ -744,7 +738,7 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
             g.z = ws == 2 ? ((g.z & keep) | val) : g.z;
             g.w = ws == 3 ? ((g.w & keep) | val) : g.w;
           }
-          stg_stream(dxp + (size_t)u * CE_NT * 8, g);
+          stg_stream(dxp + (size_t)u * NT * 8, g);
         }
       }
     }
@@ -768,13 +762,13 @@ __global__ void __launch_bounds__(CE_NT, 65536 / (CE_NT * 64)) ce_fwd_bwd_reg_ke
   }
 }
 
-template <int CL>
+template <int CL, int NT>
 static int launch_ce_reg(const __nv_bfloat16* logits, int64_t row_stride, const int64_t* labels, __nv_bfloat16* dlogits,
                          float grad_scale, int R, int V, int32_t* n_kept, float* loss, float* row_loss, unsigned int* counter,
                          cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(CE_NT);
-  cfg.dynamicSmemBytes = CE_STAGE_BYTES;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = CE_MAXC * NT * 16;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -787,16 +781,17 @@ static int launch_ce_reg(const __nv_bfloat16* logits, int64_t row_stride, const 
   // start its static share of the rows when the others are done — measured: 74 launched, 71 resident, SMs 33 % idle)
   static int max_clusters = 0;
   if (max_clusters == 0) {
-    MIMIC_CUDA_OK(cudaFuncSetAttribute(ce_fwd_bwd_reg_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(ce_fwd_bwd_reg_kernel<CL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_MAXC * NT * 16));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(ce_fwd_bwd_reg_kernel<CL, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (int)cudaSharedmemCarveoutMaxShared));
     cfg.gridDim = dim3(CL * num_sms() * 4);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ce_fwd_bwd_reg_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = num_sms() * (65536 / (CE_NT * 64)) / CL - 4;
+    if (cudaOccupancyMaxActiveClusters(&n, ce_fwd_bwd_reg_kernel<CL, NT>, &cfg) != cudaSuccess || n <= 0) n = num_sms() * (65536 / (NT * 64)) / CL - 4;
     max_clusters = n > 0 ? n : 1;
   }
   int n_clusters = max_clusters < R ? max_clusters : R;
   cfg.gridDim = dim3(n_clusters * CL);
-  MIMIC_CUDA_OK(cudaLaunchKernelEx(&cfg, ce_fwd_bwd_reg_kernel<CL>, logits, row_stride, labels, dlogits, grad_scale, R, V,
+  MIMIC_CUDA_OK(cudaLaunchKernelEx(&cfg, ce_fwd_bwd_reg_kernel<CL, NT>, logits, row_stride, labels, dlogits, grad_scale, R, V,
                                    n_kept, loss, row_loss, counter));
   return MIMIC_OK;
 }
@@ -1334,17 +1329,30 @@ __device__ __forceinline__ void st_async_f1(uint32_t remote_dst, float a, uint32
                ::"r"(remote_dst), "f"(a), "r"(remote_bar)
                : "memory");
 }
-// combine the partials of a row pair: s_z relative to m_z; s_y and A relative to m_y
-__device__ __forceinline__ void kl_merge(KlPart& t, float mz, float sz, float my, float sy, float ay) {
+// combine N <= 32 partials of a row pair (s_z relative to m_z; s_y and A relative to m_y) held in shared memory: lane i
+// takes partial i, maxima and rescaled sums go through warp shuffles (see ms_combine)
+template <int N>
+__device__ __forceinline__ void kl_combine(const KlPart* v, int lane, KlPart& t) {
   constexpr float L2E = 1.4426950408889634f;
-  const float Mz = fmaxf(t.mz, mz), My = fmaxf(t.my, my);
-  const float oz = (t.mz == -INFINITY) ? 0.f : fast_ex2((t.mz - Mz) * L2E), nz = (mz == -INFINITY) ? 0.f : fast_ex2((mz - Mz) * L2E);
-  const float oy = (t.my == -INFINITY) ? 0.f : fast_ex2((t.my - My) * L2E), ny = (my == -INFINITY) ? 0.f : fast_ex2((my - My) * L2E);
-  t.sz = t.sz * oz + sz * nz;
-  t.sy = t.sy * oy + sy * ny;
-  t.ay = t.ay * oy + ay * ny;
+  float4 a = make_float4(-INFINITY, 0.f, -INFINITY, 0.f);
+  float ay = 0.f;
+  if (lane < N) {
+    a = *reinterpret_cast<const float4*>(&v[lane]);
+    ay = v[lane].ay;
+  }
+  float Mz = a.x, My = a.z;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Mz = fmaxf(Mz, __shfl_xor_sync(0xffffffffu, Mz, o));
+    My = fmaxf(My, __shfl_xor_sync(0xffffffffu, My, o));
+  }
+  const float nMz = (Mz == -INFINITY) ? 0.f : -Mz * L2E, nMy = (My == -INFINITY) ? 0.f : -My * L2E;
+  const float f = fast_ex2(fmaf(a.z, L2E, nMy));
   t.mz = Mz;
   t.my = My;
+  t.sz = warp_sum(a.y * fast_ex2(fmaf(a.x, L2E, nMz)));
+  t.sy = warp_sum(a.w * f);
+  t.ay = warp_sum(ay * f);
 }
 
 template <int CL>
@@ -1526,12 +1534,8 @@ __global__ void __launch_bounds__(KL_NT, 2) kl_fwd_bwd_reg_kernel(const __nv_bfl
       if (lane == 0) wred[par][warp] = KlPart{wz, a, wy, b, c, 0.f, 0.f, 0.f};
     }
     __syncthreads();
-    KlPart tot = {-INFINITY, 0.f, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int wi = 0; wi < NW; ++wi) {
-      const float4 v = *reinterpret_cast<const float4*>(&wred[par][wi]);
-      kl_merge(tot, v.x, v.y, v.z, v.w, wred[par][wi].ay);
-    }
+    KlPart tot;
+    kl_combine<NW>(wred[par], lane, tot);
     if constexpr (CL > 1) {
       if (tid == 0) ptx::mbar_expect_tx(&xbar[par], CL * 20u);
       if (tid < CL) {
@@ -1540,12 +1544,7 @@ __global__ void __launch_bounds__(KL_NT, 2) kl_fwd_bwd_reg_kernel(const __nv_bfl
         st_async_f1(dst + 16, tot.ay, bar);
       }
       stage_wait(&xbar[par], (done >> 1) & 1);
-      tot = KlPart{-INFINITY, 0.f, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < CL; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(&slots[par][c]);
-        kl_merge(tot, v.x, v.y, v.z, v.w, slots[par][c].ay);
-      }
+      kl_combine<CL>(slots[par], lane, tot);
     }
     ++done;
     const float lse_z = tot.mz + __logf(tot.sz), lse_y = tot.my + __logf(tot.sy);
@@ -1796,16 +1795,20 @@ extern "C" int mimic_ce_fwd_bwd(const void* logits, int64_t logits_row_stride, i
   float* row_loss = static_cast<float*>(workspace) + 4;
   const int grid = R < num_sms() * 4 ? R : num_sms() * 4;   // measured: more CTAs beat a smaller L2 footprint
   static const bool two_pass_only = getenv("MIMIC_CE_TWO_PASS") != nullptr;      // A/B only
-  if (dtype == MIMIC_BF16 && !two_pass_only && V <= 8 * CE_NT * CE_MAXC * 8) {
-    // register-resident row: the smallest cluster whose registers hold it (7 elements of slack for the unaligned head)
+  if (dtype == MIMIC_BF16 && !two_pass_only && V <= 8 * 256 * CE_MAXC * 8) {
+    // register-resident row: one 256-thread CTA up to V = 20 480; one 512-thread CTA up to 40 960 (the 32 003-token
+    // vocabularies: no cluster exchange at all, measured 0.28 vs 0.25 of the HBM peak at 256 rows); beyond that the smallest
+    // cluster of 256-thread CTAs whose registers hold the row (0.84 vs 0.81 for 4 x 512 at 1540 x 152 000)
     const __nv_bfloat16* lg = (const __nv_bfloat16*)logits;
     __nv_bfloat16* dl = (__nv_bfloat16*)dlogits;
-    const int64_t cap1 = (int64_t)CE_NT * CE_MAXC * 8;
+    constexpr int64_t cap1 = (int64_t)256 * CE_MAXC * 8;
     int rc;
-    if (V <= cap1) rc = launch_ce_reg<1>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
-    else if (V <= 2 * cap1) rc = launch_ce_reg<2>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
-    else if (V <= 4 * cap1) rc = launch_ce_reg<4>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
-    else rc = launch_ce_reg<8>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st);
+#define MIMIC_CE_LAUNCH(CLV, NTV) launch_ce_reg<CLV, NTV>(lg, logits_row_stride, labels, dl, grad_scale, R, V, n_kept, loss, row_loss, counter, st)
+    if (V <= cap1) rc = MIMIC_CE_LAUNCH(1, 256);
+    else if (V <= 2 * cap1) rc = MIMIC_CE_LAUNCH(1, 512);
+    else if (V <= 4 * cap1) rc = MIMIC_CE_LAUNCH(4, 256);
+    else rc = MIMIC_CE_LAUNCH(8, 256);
+#undef MIMIC_CE_LAUNCH
     if (rc) return rc;
     MIMIC_LAUNCH_OK("ce_fwd_bwd_reg_kernel");
     return MIMIC_OK;

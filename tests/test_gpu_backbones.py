@@ -67,6 +67,31 @@ def _step(preset, dtype, oracle_attention, lora=False, strategies=None, upcast=F
     return model, enc, {k: float(v) for k, v in loss.items()}, grads
 
 
+def _check_gradients(dtype, tol, grads, grads_o, truth):
+    """fp32: every gradient of the CUDA-kernel step against the oracle-attention step, rel-L2 < tol.
+    bf16: a bf16 step is noisy whichever attention it uses — the oracle-attention arm itself sits up to 7.5e-2 away from the
+    same step in fp32 arithmetic on individual small parameters (a 2-element log_Z1 bias whose gradient is a cancelling
+    sum, a rank-1 LoRA A; scripts/diag_whole_step_bf16.py prints the table) — so two bf16 arms are not compared with each
+    other.  Both are measured against the TRUTH arm (the same rounded weights, fp32 arithmetic, oracle attention):
+      * all gradients together (one concatenated vector): kernels-vs-truth rel-L2 < 2e-2, and no worse than 1.5 x the
+        oracle arm's own distance;
+      * each parameter: kernels-vs-truth < 2 x oracle-vs-truth + 2e-2.
+    Kernel parity proper is tested at 1e-2 against the fp32 oracle in test_gpu_attention / test_gpu_fullsize_oracle."""
+    if dtype != torch.bfloat16:
+        errs = {n: rel(grads[n], grads_o[n]) for n in grads}
+        print("whole-step gradient rel-L2 (max):", max(errs.values()))
+        for n in grads:
+            assert errs[n] < tol, (n, errs[n])
+        return
+    cat = lambda g: torch.cat([g[n].detach().double().flatten().cpu() for n in grads])
+    all_k, all_o = rel(cat(grads), cat(truth)), rel(cat(grads_o), cat(truth))
+    print(f"whole-step bf16 gradients vs fp32-arithmetic truth: kernels {all_k:.4f}, oracle-attention arm {all_o:.4f}")
+    assert all_k < 2e-2 and all_k < 1.5 * all_o + 2e-3, (all_k, all_o)
+    for n in grads:
+        e_k, e_o = rel(grads[n], truth[n]), rel(grads_o[n], truth[n])
+        assert e_k < 2 * e_o + 2e-2, (n, e_k, e_o)
+
+
 @pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 1e-2)], ids=["fp32-d64", "bf16-d128"])
 def test_idefics_v1_layout_cross_attention_untouched(dtype, heads, tol):
     from mimic_b200.backbone import CrossAttention
@@ -74,21 +99,14 @@ def test_idefics_v1_layout_cross_attention_untouched(dtype, heads, tol):
               vocab_size=512, vision_embed_dim=64)
     model, enc, loss, grads = _step("idefics-9b", dtype, False, **kw)
     _, _, loss_o, grads_o = _step("idefics-9b", dtype, True, **kw)
+    truth = _step("idefics-9b", dtype, True, upcast=True, **kw)[3] if dtype == torch.bfloat16 else None
     # the shift hooks replaced the five self-attention forwards and none of the two cross-attention ones
     assert all(type(l.self_attn).forward is not l.self_attn.forward.__func__ for l in model.model.layers)
     assert all(g_.cross_attn.forward.__func__ is CrossAttention.forward for g_ in model.model.gated_cross_attn_layers)
     assert len(enc.attn_shift_handles) == 5 and enc.attn_shift.shape[0] == 5
     for k in ("loss", "ce_loss", "ffn_mse_loss"):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
-    errs = {n: rel(grads[n], grads_o[n]) for n in grads}
-    print("whole-step gradient rel-L2 (max):", max(errs.values()))
-    # bf16: BOTH arms are bf16 models whose attention outputs were rounded independently (tensor-core P in bf16 here, fp32
-    # softmax rounded once in the oracle arm), 48 token rows, three layers deep: this compares two noisy paths, it is not a
-    # kernel-parity bar (those sit at 1e-2 against the fp32 oracle: test_gpu_attention / test_gpu_fullsize_oracle).
-    # Measured worst cases 2.2e-2 (a rank-1 LoRA A) and 2.9e-2 (a 2-element log_Z1 bias: a signed sum that cancels): 4e-2.
-    for n in grads:
-        bar = tol if dtype != torch.bfloat16 else 4 * tol
-        assert errs[n] < bar, (n, errs[n])
+    _check_gradients(dtype, tol, grads, grads_o, truth)
 
 
 @pytest.mark.parametrize("dtype,heads,tol", [(torch.float32, 4, 2e-4), (torch.bfloat16, 2, 1e-2)], ids=["fp32-d64", "bf16-d128"])
@@ -97,19 +115,12 @@ def test_llava_layout_with_lora_and_qkv_bias(dtype, heads, tol):
               vocab_size=1000)
     model, enc, loss, grads = _step("llava-interleave-7b", dtype, False, lora=True, **kw)
     _, _, loss_o, grads_o = _step("llava-interleave-7b", dtype, True, lora=True, **kw)
+    truth = _step("llava-interleave-7b", dtype, True, lora=True, upcast=True, **kw)[3] if dtype == torch.bfloat16 else None
     assert model.language_model.model.layers[0].self_attn.q_proj.bias is not None
     assert sum(1 for n in grads if ".lora_" in n) == 6
     for k in ("loss", "ce_loss", "ffn_mse_loss"):
         assert abs(loss[k] - loss_o[k]) < tol * abs(loss_o[k]) + 1e-7, k
-    errs = {n: rel(grads[n], grads_o[n]) for n in grads}
-    print("whole-step gradient rel-L2 (max):", max(errs.values()))
-    # bf16: BOTH arms are bf16 models whose attention outputs were rounded independently (tensor-core P in bf16 here, fp32
-    # softmax rounded once in the oracle arm), 48 token rows, three layers deep: this compares two noisy paths, it is not a
-    # kernel-parity bar (those sit at 1e-2 against the fp32 oracle: test_gpu_attention / test_gpu_fullsize_oracle).
-    # Measured worst cases 2.2e-2 (a rank-1 LoRA A) and 2.9e-2 (a 2-element log_Z1 bias: a signed sum that cancels): 4e-2.
-    for n in grads:
-        bar = tol if dtype != torch.bfloat16 else 4 * tol
-        assert errs[n] < bar, (n, errs[n])
+    _check_gradients(dtype, tol, grads, grads_o, truth)
 
 
 def test_attn_record_point_config():
