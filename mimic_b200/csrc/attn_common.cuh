@@ -27,6 +27,7 @@ struct AttnParams {
   int debug_flags = 0;
   unsigned long long* trace = nullptr;   // optional in-kernel timeline (mimic_debug_set_trace), CTA (0,0,0) only
   float dq_seed_mul = 1.f, dq_out_mul = 1.f;   // dq_acc seed = dz*w*seed_mul; dq = dq_acc*out_mul
+  int dq_direct = 0;                           // tcgen05 backward with ONE key tile (S <= 128): dq leaves the main kernel as bf16
 };
 
 unsigned long long* debug_trace_buffer();

@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(128, 6) attn_bwd_prep_kernel(AttnParams p) {
           p.dz_ws[row0 + t] = dz_all;
           p.delta_ws[row0 + t] = dl;
         }
-        float* dqa = p.dq_acc + (row0 + t) * D + c0;
+        if (!p.dq_direct) {                                  // (one key tile: the main kernel adds dz * w itself and writes bf16 dq)
+          float* dqa = p.dq_acc + (row0 + t) * D + c0;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) dqa[e] = dz * wv[e];   // dq seed (zero for an inactive handle)
+          for (int e = 0; e < EPL; ++e) dqa[e] = dz * wv[e];   // dq seed (zero for an inactive handle)
+        }
         if (p.active) {
 #pragma unroll
           for (int e = 0; e < EPL; ++e) {

@@ -548,6 +548,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       const bool dtr = (warp == 18 && lane == 0);
       if (dtr) stamp(4, i, 0);
+      // one key tile (S <= 128, the query pass): no other CTA adds to these dq rows, so they leave as bf16 from here —
+      // dq = scale * dQ + dz * w[h] — and neither the fp32 accumulator, its seed, nor the conversion launch exist.
+      // dz of the tile's 64 rows and this thread's w column are fetched before the wait.
+      float dz_lo = 0.f, dz_hi = 0.f, w_c = 0.f;
+      if (p.dq_direct && p.active) {
+        const int64_t r0 = ((int64_t)b * p.H + h) * T + qt * BQ;
+        if (qt * BQ + lane < T) dz_lo = p.dz_ws[r0 + lane];
+        if (qt * BQ + 32 + lane < T) dz_hi = p.dz_ws[r0 + 32 + lane];
+        w_c = p.w[h * HD + c];
+      }
       mbar_wait(&bars[DQ_FULL + st], (i >> 1) & 1, 410 + st);
       if (dtr) stamp(4, i, 1);
       tc_fence_after();
@@ -559,6 +569,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_arrive(&bars[DRAIN_DONE + st]);              // dP[st] may take dP^T(i+2) / dS^T(i+2)
       if (dtr) stamp(4, i, 2);
       if (dbg(256)) continue;
+      if (p.dq_direct) {
+        __nv_bfloat16* dqp = reinterpret_cast<__nv_bfloat16*>(p.dq) + (((int64_t)b * p.H + h) * T + qt * BQ) * HD + c;
+        const int rows_left = T - qt * BQ;               // (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s0 = __shfl_sync(0xffffffffu, dz_lo, j), s1 = __shfl_sync(0xffffffffu, dz_hi, j);
+          if (j < rows_left) dqp[(int64_t)j * HD] = __float2bfloat16_rn(fmaf(p.dq_out_mul, v0[j], s0 * w_c));
+          if (32 + j < rows_left) dqp[(int64_t)(32 + j) * HD] = __float2bfloat16_rn(fmaf(p.dq_out_mul, v1[j], s1 * w_c));
+        }
+        if (dtr) stamp(4, i, 3);
+        continue;
+      }
       // Each drain warp reduces its own 32-column slice of dQ on its own: four 16-row chunks through two 2 KB staging
       // buffers of the warp, one TMA tile reduce-add (fp32 add at L2) per chunk.  No barrier couples the four warps, and
       // while the TMA unit reads one buffer the lanes fill the other.  (Measured: skipping the waits or the fences changes nothing; the
@@ -601,6 +623,11 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   pp.trace = debug_trace_capacity() >= 24 * 64 ? debug_trace_buffer() : nullptr;
   static const int dbg_env = [] { const char* e = getenv("MIMIC_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();   // bit 0: skip the dQ reduce (timing experiments only)
   pp.debug_flags = dbg_env;
+  static const bool no_direct = getenv("MIMIC_BWD_NO_DIRECT_DQ") != nullptr;   // A/B only
+  // one key tile whose CTA visits EVERY query tile (with T > S the first query tiles of an inactive causal handle see no key
+  // and are skipped: their dq rows only exist through the accumulator path), no outside gradient on lse_full (the seed
+  // uses the op's own dz, dz_ws holds the combined one)
+  pp.dq_direct = (p.S <= BN && (p.active || !p.causal || p.S >= p.T) && p.d_lse_full == nullptr && !no_direct) ? 1 : 0;
   if ((rc = simt::bwd_prep_bf16_d128(pp, st))) return rc;
   CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   if ((rc = make_map_f32_rows(&tdq, p.dq_acc, (int64_t)p.B * p.H, p.T, 16))) return rc;
@@ -622,7 +649,7 @@ int bwd(const AttnParams& p, cudaStream_t st) {
   if (pp.trace != nullptr || pp.debug_flags != 0) attn_bwd_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp, life);
   else attn_bwd_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdk, tdv, tdq, pp, 0);
   MIMIC_LAUNCH_OK("attn_bwd_tc_kernel");
-  return simt::convert_dq_bf16(pp, st);
+  return pp.dq_direct ? MIMIC_OK : simt::convert_dq_bf16(pp, st);
 }
 
 }  // namespace tc

@@ -1,5 +1,5 @@
 """Kernel-level sweep (BASELINE config 5 + the HBM-bound kernels): CUDA-event timing of every kernel family
-through the C ABI, >= 20 reps after warm-up, L2 flushed between reps for the HBM-bound kernels, the reference's
+through the C ABI, >= 20 reps after warm-up, L2 flushed between reps for the HBM-bound kernels (flush_l2), the reference's
 own PyTorch path (SDPA + do_shift) on the same GPU for comparison.  Writes gpurun_out/kernel_sweep.json."""
 import json
 import math
@@ -14,7 +14,19 @@ from oracle import shifted_attention as OA  # noqa: E402
 
 PEAK = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 dev = "cuda"
-flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+FLUSH = os.environ.get("SWEEP_FLUSH", "read")
+
+
+def flush_l2():
+    """Evict the kernel's inputs from the 126 MB L2 before a rep.  "read" (default): stream 256 MB through L2 with a
+    reduction — the cache is left full of CLEAN lines.  "write" (round 1's protocol): memset 256 MB — the cache is left
+    full of DIRTY lines whose write-back (up to 126 MB) then lands inside the timed kernel: a 200 MB kernel measured
+    58 us after a write flush and 42 us under ncu / after a read flush."""
+    if FLUSH == "write":
+        flush_buf.zero_()
+    else:
+        flush_buf.view(torch.float32).sum()
 
 
 def time_kernel(fn, key, reps=20, warm=3):
@@ -26,7 +38,7 @@ def time_kernel(fn, key, reps=20, warm=3):
     ops.timer.enabled = True
     ops.timer.reset()
     for _ in range(reps):
-        flush_buf.zero_()
+        flush_l2()
         fn()
     torch.cuda.synchronize()
     ops.timer.enabled = False
@@ -40,7 +52,7 @@ def timeit(fn, reps=20, warm=3, flush=False):
     tot = 0.0
     for _ in range(reps):
         if flush:
-            flush_buf.zero_()
+            flush_l2()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
