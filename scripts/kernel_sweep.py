@@ -21,8 +21,9 @@ FLUSH = os.environ.get("SWEEP_FLUSH", "read")
 def flush_l2():
     """Evict the kernel's inputs from the 126 MB L2 before a rep.  "read" (default): stream 256 MB through L2 with a
     reduction — the cache is left full of CLEAN lines.  "write" (round 1's protocol): memset 256 MB — the cache is left
-    full of DIRTY lines whose write-back (up to 126 MB) then lands inside the timed kernel: a 200 MB kernel measured
-    58 us after a write flush and 42 us under ncu / after a read flush."""
+    full of DIRTY lines whose write-back lands inside the timed kernel.  Measured on the same box
+    (profiles/r02_kernel_sweep_hbm_{read,write}flush.json): MSE 0.56 vs 0.52 of the HBM peak at 201 MB, 0.86 vs 0.82 at
+    3.2 GB; CE 0.86 vs 0.84; gather 0.95 vs 0.81 at 134 MB."""
     if FLUSH == "write":
         flush_buf.zero_()
     else:
@@ -43,6 +44,34 @@ def time_kernel(fn, key, reps=20, warm=3):
     torch.cuda.synchronize()
     ops.timer.enabled = False
     return ops.timer.summary()[key][1]
+
+
+def time_in_graph(fns, rounds=5):
+    """Per-call device time the way the step runs a kernel: inside a CUDA graph.  `fns` = the same op on DIFFERENT buffer
+    sets (together larger than L2, so no call finds its inputs cached); rounds x len(fns) calls captured back to back,
+    one event pair around a replay.  No launch latency, no host gap between the event and the kernel — which is what the
+    event bracket of a single small launch mostly measures (MSE at 201 MB: 55 us bracketed, 42 us under ncu)."""
+    gr, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for fn in fns:
+            fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(rounds):
+                for fn in fns:
+                    fn()
+    torch.cuda.synchronize()
+    gr.replay()
+    best = None
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        gr.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / (rounds * len(fns))
+        best = ms if best is None else min(best, ms)
+    return best
 
 
 def timeit(fn, reps=20, warm=3, flush=False):
@@ -112,7 +141,13 @@ def mse(L, rows, D, dtype=torch.bfloat16):
     fn = lambda: ops.align_mse(hs, hp, r2c, rw)
     ms = time_kernel(fn, "mse_fwd_bwd")
     nbytes = 3 * L * rows * D * hp.element_size()
-    return {"L": L, "rows": rows, "D": D, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+    r = {"L": L, "rows": rows, "D": D, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+    if nbytes < 1e9:                       # the step's shape: also as the step runs it (4 buffer sets = 0.8 GB)
+        sets = [([torch.randn(rows, D, device=dev).to(dtype).requires_grad_(True) for _ in range(L)],
+                 torch.randn(L, rows, D, device=dev).to(dtype)) for _ in range(4)]
+        g_ms = time_in_graph([(lambda a=a, b=b: ops.align_mse(a, b, r2c, rw)) for a, b in sets])
+        r.update(ms_in_graph=g_ms, frac_of_hbm_in_graph=nbytes / g_ms / 1e6 / PEAK["hbm_gbs"])
+    return r
 
 
 def cos(L, rows, D, dtype=torch.bfloat16):
@@ -140,7 +175,12 @@ def ce(R, V):
     fn = lambda: ops.ce_loss(logits, labels)
     ms = time_kernel(fn, "ce_fwd_bwd")
     nbytes = 2 * R * V * 2
-    return {"R": R, "V": V, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+    r = {"R": R, "V": V, "ms": ms, "algorithmic_MB": nbytes / 1e6, "gbs": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PEAK["hbm_gbs"]}
+    if nbytes < 1e8:                       # the Idefics2 step's shape: also as the step runs it (12 buffer sets = 0.4 GB)
+        sets = [(torch.randn(R, V, device=dev) * 2).bfloat16().requires_grad_(True) for _ in range(12)]
+        g_ms = time_in_graph([(lambda a=a: ops.ce_loss(a, labels)) for a in sets], rounds=2)
+        r.update(ms_in_graph=g_ms, frac_of_hbm_in_graph=nbytes / g_ms / 1e6 / PEAK["hbm_gbs"])
+    return r
 
 
 def norm_shift(N, D):
