@@ -204,64 +204,105 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const void* const* __r
   }
 }
 
-// Variant: one (layer, row) item per WARP.  Every warp runs an independent index -> load -> store chain, so
-// 32+ chains per SM overlap their latencies; 4 x 16-byte loads per array in flight per lane.
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) mse_fwd_bwd_warp_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
-                                                               const T* __restrict__ hp,
+// Pipelined variant for rows of <= 512 chunks (D <= 4096: every BASELINE backbone), bf16.  The generic kernel above runs,
+// per item, a chain of three dependent global loads (row -> compact index -> weight, layer -> pointer) before the first
+// byte of the row is requested, and requests the next item's rows only after the current gradient is stored.  Here the
+// compact index is fetched TWO items ahead, the weight and the rows ONE item ahead (raw bf16 chunks, 16 registers per
+// item in flight), and the layer pointers sit in shared memory: while an item is reduced and its gradient stored the next
+// item's 16 KB are already on their way.
+__global__ void __launch_bounds__(256) mse_fwd_bwd_pipe_kernel(const void* const* __restrict__ h_ptrs, int64_t h_row_stride,
+                                                               const __nv_bfloat16* __restrict__ hp,
                                                                const int32_t* __restrict__ row_to_compact,
                                                                const float* __restrict__ row_w,
                                                                void* const* __restrict__ dh_ptrs, float grad_scale, int L,
                                                                int rows, int N, int D, float* __restrict__ partial,
                                                                unsigned int* __restrict__ counter, float* __restrict__ loss) {
+  using T = __nv_bfloat16;
+  constexpr int MAXL = 128;
   __shared__ float red[32];
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  __shared__ const T* s_h[MAXL];
+  __shared__ T* s_dh[MAXL];
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    s_h[l] = reinterpret_cast<const T*>(h_ptrs[l]);
+    s_dh[l] = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) : nullptr;
+  }
+  __syncthreads();
   const int chunks = D / 8;
-  const int64_t items = (int64_t)L * rows;
-  float acc = 0.f;
-  for (int64_t it = (int64_t)blockIdx.x * wpb + wib; it < items; it += (int64_t)gridDim.x * wpb) {
+  const int64_t items = (int64_t)L * rows, g = gridDim.x;
+  const int ch_a = threadIdx.x, ch_b = threadIdx.x + 256;
+  const bool has_a = ch_a < chunks, has_b = ch_b < chunks;
+  auto compact_of = [&](int64_t it) { return it < items ? row_to_compact[(int)(it % rows)] : -1; };
+  struct Rows {
+    uint4 ha, hb, ta, tb;
+  };
+  auto request = [&](int64_t it, int c, Rows& x) {      // the item's rows of H and H' (nothing for an unselected row)
+    if (c < 0) return;
     const int l = (int)(it / rows), r = (int)(it % rows);
-    const int c = row_to_compact[r];
-    T* dh = dh_ptrs ? reinterpret_cast<T*>(dh_ptrs[l]) + (int64_t)r * D : nullptr;
-    if (c < 0) {
-      if (dh) {
-        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int ch = lane; ch < chunks; ch += 32) Chunk<T>::store(dh + ch * 8, z);
-      }
-      continue;
-    }
-    const T* h = reinterpret_cast<const T*>(h_ptrs[l]) + (int64_t)r * h_row_stride;
+    const T* h = s_h[l] + (int64_t)r * h_row_stride;
     const T* t = hp + ((int64_t)l * N + c) * D;
-    const float w = row_w[c];
-    const float gw = 2.f * w * grad_scale;
-    float s = 0.f;
-    for (int ch0 = lane; ch0 < chunks; ch0 += 32 * UNROLL) {
-      float a[UNROLL][8], b[UNROLL][8];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int ch = ch0 + u * 32;
-        if (ch < chunks) {
-          Chunk<T>::load(h + ch * 8, a[u]);
-          Chunk<T>::load(t + ch * 8, b[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int ch = ch0 + u * 32;
-        if (ch < chunks) {
-          float g[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float df = a[u][e] - b[u][e];
-            s += df * df;
-            g[e] = gw * df;
-          }
-          if (dh) Chunk<T>::store(dh + ch * 8, g);
-        }
-      }
+    if (has_a) {
+      x.ha = ldg_stream(h + ch_a * 8);
+      x.ta = ldg_stream(t + ch_a * 8);
     }
-    acc += w * s;
+    if (has_b) {
+      x.hb = ldg_stream(h + ch_b * 8);
+      x.tb = ldg_stream(t + ch_b * 8);
+    }
+  };
+  auto diff_chunk = [&](const uint4& hv, const uint4& tv, float gw, float& ssq, uint4& out) {
+    Raw8<T> a, b;
+    a.u = hv;
+    b.u = tv;
+    float fa[8], fb[8], gch[8];
+    a.unpack(fa);
+    b.unpack(fb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float df = fa[e] - fb[e];
+      ssq = fmaf(df, df, ssq);
+      gch[e] = gw * df;
+    }
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(gch[2 * e], gch[2 * e + 1]);
+  };
+  float acc = 0.f;
+  int64_t it = blockIdx.x;
+  int c0 = compact_of(it), c1 = compact_of(it + g);
+  float w0 = c0 >= 0 ? row_w[c0] : 0.f;
+  Rows x0 = {}, x1 = {};
+  request(it, c0, x0);
+  for (; it < items; it += g) {
+    const int c2 = compact_of(it + 2 * g);               // in flight during this item
+    const float w1 = c1 >= 0 ? row_w[c1] : 0.f;          // c1 arrived an item ago
+    request(it + g, c1, x1);                             // the next item's rows travel while this one is worked on
+    const int l = (int)(it / rows), r = (int)(it % rows);
+    T* dh = s_dh[l] ? s_dh[l] + (int64_t)r * D : nullptr;
+    if (c0 < 0) {
+      if (dh) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (has_a) stg_stream(dh + ch_a * 8, z);
+        if (has_b) stg_stream(dh + ch_b * 8, z);
+      }
+    } else {
+      const float gw = 2.f * w0 * grad_scale;
+      float ssq = 0.f;
+      uint4 ga, gb;
+      if (has_a) {
+        diff_chunk(x0.ha, x0.ta, gw, ssq, ga);
+        if (dh) stg_stream(dh + ch_a * 8, ga);
+      }
+      if (has_b) {
+        diff_chunk(x0.hb, x0.tb, gw, ssq, gb);
+        if (dh) stg_stream(dh + ch_b * 8, gb);
+      }
+      acc = fmaf(w0, ssq, acc);
+    }
+    c0 = c1;
+    w0 = w1;
+    x0 = x1;
+    c1 = c2;
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) {
@@ -1755,18 +1796,12 @@ extern "C" int mimic_mse_fwd_bwd(const void* const* h_ptrs, int64_t h_row_stride
   const int grid = mse_grid(L, rows);
   float* partial = static_cast<float*>(workspace) + 4;
   unsigned int* counter = static_cast<unsigned int*>(workspace);   // zero on first use; the kernel leaves it zero
-  static const int variant = getenv("MIMIC_MSE_VARIANT") ? atoi(getenv("MIMIC_MSE_VARIANT")) : 3;   // 3 measured best (79% of HBM peak)
-  if (h_dtype == MIMIC_BF16 && variant == 1)
-    mse_fwd_bwd_warp_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
-                                                                    row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
-  else if (h_dtype == MIMIC_BF16 && variant == 2)
-    mse_fwd_bwd_warp_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
-                                                                    row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
-  else if (h_dtype == MIMIC_BF16 && variant == 3)
-    mse_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
-                                                               row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
+  static const bool no_pipe = getenv("MIMIC_MSE_NO_PIPE") != nullptr;      // A/B only
+  if (h_dtype == MIMIC_BF16 && D <= 4096 && L <= 128 && !no_pipe)
+    mse_fwd_bwd_pipe_kernel<<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact, row_w,
+                                                  dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
   else if (h_dtype == MIMIC_BF16)
-    mse_fwd_bwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
+    mse_fwd_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const __nv_bfloat16*)hp, row_to_compact,
                                                                row_w, dh_ptrs, grad_scale, L, rows, N, D, partial, counter, loss);
   else if (h_dtype == MIMIC_F32)
     mse_fwd_bwd_kernel<float, 2><<<grid, 256, 0, st>>>(h_ptrs, h_row_stride, (const float*)hp, row_to_compact, row_w,
