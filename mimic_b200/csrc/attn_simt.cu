@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnParams p) {
 // its columns of mu*g and dz*q to per-lane column accumulators on the spot.  (The first version made a second pass over g
 // and q, column-wise per thread, for these sums: 0.27 ms at the T = 4096 sweep shape, a tenth of the whole backward, against
 // ~0.1 ms for its bytes.)  Per CTA: the four warps' column sums meet in shared memory, ONE atomicAdd per (CTA, h, c).
+// (Tried in round 2 and measured slower, 0.85 vs 0.80 ms at T = 512 and 3.01 vs 2.82 ms at T = 4096 for the whole backward:
+// prefetching the next group of four rows into a second set of registers — it needs ~120 registers, i.e. 4 instead of 6
+// CTAs per SM, and still spills.)
 // ROWS query rows per CTA: 64 for long sequences (few atomics per parameter), 16 when the whole problem is a few thousand
 // rows (a MimIC query pass: T = 128) and the launch is pure latency.
 template <typename E, int EPL>

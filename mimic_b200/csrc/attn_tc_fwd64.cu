@@ -491,7 +491,8 @@ int fwd64(const AttnParams& p, cudaStream_t st) {
   size_t smem = smem_bytes(p.S);
   // diagnosis only: MIMIC_FWD_ONE_CTA pads the request so that a single CTA fits an SM — how much of the two-CTA rate one CTA
   // alone reaches tells how well the pair overlaps (the convoy question)
-  if (getenv("MIMIC_FWD_ONE_CTA") && smem + (120u << 10) <= (227u << 10)) smem += 120u << 10;
+  static const bool one_cta = getenv("MIMIC_FWD_ONE_CTA") != nullptr;      // (read once)
+  if (one_cta && smem + (120u << 10) <= (227u << 10)) smem += 120u << 10;
   static size_t configured = 0;
   if (smem > configured) {
     MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
