@@ -24,6 +24,13 @@ sh, w, b = torch.randn(H, d, device="cuda"), torch.randn(H, d, device="cuda") * 
 for _ in range(REPS):
     out, lse_c, lse_f, mu, saved = ops.shifted_attention_forward(q, k, v, None, sh, w, b, causal=True, active=True, scale=d ** -0.5)
     ops.shifted_attention_backward(saved, out, do, lse_c, lse_f, mu, causal=True, active=True, scale=d ** -0.5)
+# the query pass of the step: B = 2, GQA 32:8, T = S = 128, active (single-tile forward; backward with the direct dq path)
+q2 = torch.randn(2, H, 128, d, device="cuda").bfloat16()
+k2, v2 = (torch.randn(2, 8, 128, d, device="cuda").bfloat16() for _ in range(2))
+do2 = torch.randn(2, 128, H, d, device="cuda").bfloat16()
+for _ in range(REPS):
+    out2, lc2, lf2, mu2, saved2 = ops.shifted_attention_forward(q2, k2, v2, None, sh, w, b, causal=True, active=True, scale=d ** -0.5)
+    ops.shifted_attention_backward(saved2, out2, do2, lc2, lf2, mu2, causal=True, active=True, scale=d ** -0.5)
 # alignment loss, bandwidth regime: L=32, 4096 rows, D=4096 (3.2 GB algorithmic) and the step shape (201 MB)
 for rows in (4096, 256):
     hs = [torch.randn(rows, 4096, device="cuda").bfloat16().requires_grad_(True) for _ in range(32)]
