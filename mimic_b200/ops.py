@@ -511,6 +511,19 @@ def align_cos(hs: Sequence[torch.Tensor], hp: torch.Tensor, row_to_compact: torc
     return _AlignCos.apply(hp, row_to_compact, row_w, grad_scale, assume_folded, *hs)
 
 
+def _grad_like(x: torch.Tensor) -> torch.Tensor:
+    """Gradient buffer for a [R, V] row view: SAME row stride and the same address modulo 32 bytes as `x` (the loss kernels
+    address logits and gradient with one stride and vector-align their chunks on the logits row)."""
+    if x.is_contiguous() and x.data_ptr() % 32 == 0:
+        return torch.empty_like(x)
+    R, V = x.shape
+    es = x.element_size()
+    n = (R - 1) * x.stride(0) + V
+    buf = torch.empty(n + 32 // es, dtype=x.dtype, device=x.device)
+    off = ((x.data_ptr() - buf.data_ptr()) % 32) // es
+    return buf.as_strided((R, V), (x.stride(0), 1), off)
+
+
 class _KLLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, y, y_row, grad_scale, assume_folded, inplace):
@@ -526,7 +539,7 @@ class _KLLoss(torch.autograd.Function):
         assert y_row.numel() == R and yy.dtype == zz.dtype
         dev = zz.device
         need_grad = ctx.needs_input_grad[0]
-        dz = (zz if inplace else torch.empty_like(zz)) if need_grad else None
+        dz = (zz if inplace else _grad_like(zz)) if need_grad else None
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         n_rows = torch.empty(1, dtype=torch.int32, device=dev)
         nbytes = lib.mimic_ce_workspace(R)
@@ -550,7 +563,7 @@ class _KLLoss(torch.autograd.Function):
             return (None,) * 6
         if not ctx.assume_folded:
             d = d * _unfold(g, ctx.grad_scale).to(d.dtype)
-        return d.view(ctx.shape), None, None, None, None, None
+        return d.reshape(ctx.shape), None, None, None, None, None
 
 
 def kl_loss(shift_logits: torch.Tensor, prefix_logits: torch.Tensor, prefix_row: torch.Tensor, grad_scale: float = 1.0,
@@ -576,7 +589,7 @@ class _CELoss(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         dlog = None
         if need_grad:
-            dlog = lg if inplace else torch.empty_like(lg)
+            dlog = lg if inplace else _grad_like(lg)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         n_kept = torch.empty(1, dtype=torch.int32, device=dev)
         nbytes = lib.mimic_ce_workspace(R)
@@ -599,7 +612,7 @@ class _CELoss(torch.autograd.Function):
             return None, None, None, None, None
         if not ctx.assume_folded:
             d = d * _unfold(g, ctx.grad_scale).to(d.dtype)
-        return d.view(ctx.shape), None, None, None, None
+        return d.reshape(ctx.shape), None, None, None, None
 
 
 def ce_loss(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, assume_folded: bool = False,

@@ -315,3 +315,42 @@ def test_adamw_scale_lr_group_matches_torch():
         for prm, mk in zip(params, masks):
             want[mk] = prm.detach()
         assert rel(p, want) < 1e-6
+
+
+@pytest.mark.parametrize("V", [1000, 32003, 60001], ids=["V1000", "V32003", "V60001"])
+def test_ce_kl_strided_offset_rows_many_rows_per_cluster(V):
+    """The register / cluster kernels stage every row with a bulk copy whose source must be 16-byte aligned: rows that
+    are views into a wider buffer (row stride > V, odd element offset of the first row), more rows than resident clusters
+    (every cluster walks several rows: stage re-arming, barrier phases), ignored rows in a row (nothing staged for them)."""
+    from mimic_b200 import ops
+    g = torch.Generator().manual_seed(V)
+    R, pad = (700 if V <= 1000 else 150), 13
+    wide = (torch.randn(R + 1, V + pad, generator=g) * 3).bfloat16()
+    wide_y = (torch.randn(R + 1, V + 2 * pad + 1, generator=g) * 3).bfloat16()
+    labels = torch.randint(0, V, (R,), generator=g)
+    labels[5:40] = -100                                    # a run of ignored rows, longer than one cluster's stride can skip
+    labels[::9] = -100
+    wide_c, wide_yc = wide.cuda(), wide_y.cuda()
+    z = wide_c[1:, 3:3 + V]                                # row stride V + 13, first element at an odd offset
+    y = wide_yc[:-1, 8:8 + V]
+    assert z.stride(0) == V + pad and z.stride(1) == 1
+    # CE
+    l32 = wide[1:, 3:3 + V].float().requires_grad_(True)
+    want = F.cross_entropy(l32, labels, ignore_index=-100)
+    wg, = torch.autograd.grad(want, l32)
+    zc = z.detach().requires_grad_(True)
+    loss = ops.ce_loss(zc, labels.cuda())
+    got, = torch.autograd.grad(loss, zc)
+    assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want)) + 1e-6
+    assert rel(got, wg) < 1e-2 and float(got[labels.cuda() < 0].abs().max()) == 0.0
+    # KL against rows of the other buffer
+    sel = labels >= 0
+    y_row = torch.where(sel, torch.randperm(R, generator=g), torch.full((R,), -1)).to(torch.int32)
+    z32 = wide[1:, 3:3 + V].float().requires_grad_(True)
+    want = OL.logits_kl(z32[sel], wide_y[:-1, 8:8 + V].float()[y_row[sel].long()])
+    wg, = torch.autograd.grad(want, z32)
+    zc = z.detach().requires_grad_(True)
+    loss = ops.kl_loss(zc, y, y_row.cuda())
+    got, = torch.autograd.grad(loss, zc)
+    assert abs(float(loss) - float(want)) < 1e-4 * abs(float(want)) + 1e-6
+    assert rel(got, wg) < 1e-2 and float(got[~sel.cuda()].abs().max()) == 0.0
