@@ -447,7 +447,8 @@ def _align_forward(ctx, kind, hp, row_to_compact, row_w, grad_scale, assume_fold
     h0 = hs[0]
     D = h0.shape[-1]
     rows = h0.numel() // D
-    hs = [h if (h.is_contiguous()) else h.contiguous() for h in hs]
+    # rows are read as 16-byte vectors: contiguous and 16-byte aligned (a contiguous view at an odd offset is copied)
+    hs = [(h if h.data_ptr() % 16 == 0 else h.clone()) if h.is_contiguous() else h.contiguous() for h in hs]
     N = hp.shape[1]
     dev = h0.device
     need_grad = any(ctx.needs_input_grad[5:])
