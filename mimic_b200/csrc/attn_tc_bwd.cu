@@ -496,6 +496,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     {
       // dV / dK leave through shared memory (the K and V tiles are dead once DKV_FULL fired) and four TMA tile stores:
       // thread-per-row global stores touch 32 different lines per warp instruction (~4000 sector writes per CTA).
+      // (Measured again in round 2, A/B in one process: writing the half rows straight from registers so that the CTA
+      // need not wait ~1.3 us for the TMA unit to drain the four boxes is SLOWER — 0.859 vs 0.803 ms at T = 512,
+      // 1.129 vs 1.069 at T = 1024.)
       const int which = g;                               // 0: dV -> the V tile's smem, 1: dK -> the K tile's
       const int half = hf;                               // 64-column half of the row = one [128 rows][128 B] TMA box
       const float mul = which ? p.scale : 1.f;
