@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MIMIC_ABI_VERSION 1
+#define MIMIC_ABI_VERSION 2
 #define MIMIC_API __attribute__((visibility("default")))
 
 enum { MIMIC_OK = 0, MIMIC_ERR_ARG = 1, MIMIC_ERR_CUDA = 2, MIMIC_ERR_UNSUPPORTED = 3 };
@@ -261,8 +261,12 @@ MIMIC_API int mimic_rope_qk(const void* q, int64_t q_sb, int64_t q_st, int64_t q
  * src/shift_model.py:306-372: names containing "bias" get 0).  Replaces DeepSpeedCPUAdam's host
  * round trip.  What changes per step arrives in device memory so a captured CUDA graph can replay it:
  *   hyper: fp32 [3] = { lr, 1 - beta1^step, sqrt(1 - beta2^step) }.
- *   sumsq: fp32 [1] workspace.  grad is scaled in place by grad_mul (1/world, 1/accum) first.
+ *   sumsq: workspace of mimic_adamw_workspace() bytes, zero on first use (the kernels leave it reusable); its first
+ *          float holds the squared gradient norm after the call.  The norm is summed in a FIXED order (per-CTA
+ *          partials added by the last CTA): ranks holding bit-identical gradients clip by the same factor.
+ *          grad is scaled in place by grad_mul (1/world, 1/accum) first.
  * ------------------------------------------------------------------------------------------ */
+MIMIC_API size_t mimic_adamw_workspace(void);
 MIMIC_API int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                      const float* weight_decay, int64_t n, const float* hyper, float beta1, float beta2,
                      float eps, float grad_mul, float max_norm, float* sumsq, void* stream);

@@ -29,6 +29,7 @@ class AttnDesc(C.Structure):
 EXPORTS = {
     # name: (restype, argtypes)
     "mimic_abi_version": (C.c_int, []),
+    "mimic_adamw_workspace": (C.c_size_t, []),
     "mimic_last_error": (C.c_char_p, []),
     "mimic_last_attn_impl": (C.c_char_p, []),
     "mimic_debug_set_trace": (None, [C.c_void_p, C.c_size_t]),
@@ -100,8 +101,8 @@ def _load() -> C.CDLL:
         import warnings
         warnings.warn(f"binding a STALE libmimic_b200.so (MIMIC_ALLOW_STALE_LIB set); rebuild failed: {e}", RuntimeWarning)
     lib = _bind(LIB_PATH)             # AttributeError when a prebuilt library is older than the header
-    if lib.mimic_abi_version() != 1:
-        raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 1; rebuild (python -m mimic_b200.build --force)")
+    if lib.mimic_abi_version() != 2:
+        raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 2; rebuild (python -m mimic_b200.build --force)")
     return lib
 
 

@@ -1715,8 +1715,14 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(const T* __restrict__ q, i
 
 // ---------------------------------------------------------------------------------------------
 // clip + AdamW on the flat fp32 parameter buffer
-__global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ grad, int64_t n, float grad_mul, float* __restrict__ sumsq) {
+// Sum of squares of the (scaled) gradient, DETERMINISTIC: per-CTA partials (fixed strided order inside a CTA) go to the
+// workspace, the last CTA to arrive adds them in index order.  A float atomicAdd per CTA made the clip coefficient depend
+// on the arrival order: two data-parallel ranks holding bit-identical all-reduced gradients then clipped by factors one
+// ulp apart and their parameters drifted apart (tests/test_gpu_dp_nccl.py caught it on one box of the pool).
+//   ws[0] = sum (result)   ws[1] = arrival counter (uint32, self-resetting)   ws[2 ...] = per-CTA partials
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ grad, int64_t n, float grad_mul, float* __restrict__ ws) {
   __shared__ float red[32];
+  __shared__ bool is_last;
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float g = grad[i] * grad_mul;
@@ -1724,7 +1730,23 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(float* __restrict__ gra
     acc += g * g;
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(sumsq, acc);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws + 1);
+  if (threadIdx.x == 0) {
+    ws[2 + blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(ws + 2 + i);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      ws[0] = tot;
+      *counter = 0u;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
@@ -2001,6 +2023,10 @@ extern "C" int mimic_rope_qk(const void* q, int64_t q_sb, int64_t q_st, int64_t 
   return MIMIC_OK;
 }
 
+extern "C" size_t mimic_adamw_workspace(void) {
+  return (size_t)(2 + 4 * num_sms()) * sizeof(float);   // sum, arrival counter, one partial per CTA of the norm kernel
+}
+
 extern "C" int mimic_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* weight_decay,
                                 int64_t n, const float* hyper, float beta1, float beta2, float eps, float grad_mul,
                                 float max_norm, float* sumsq, void* stream) {
@@ -2015,7 +2041,6 @@ extern "C" int mimic_adamw_step_groups(float* param, float* grad, float* exp_avg
   MIMIC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && weight_decay && hyper && sumsq, "NULL argument");
   MIMIC_CHECK_ARG(n > 0, "bad n");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MIMIC_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(float), st));
   const int grid = (int)((n + 255) / 256 < (int64_t)num_sms() * 4 ? (n + 255) / 256 : (int64_t)num_sms() * 4);
   grad_sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_mul, sumsq);
   MIMIC_LAUNCH_OK("grad_sumsq_kernel");

@@ -629,6 +629,11 @@ def adamw_hyper(lr: float, step: int, betas=(0.9, 0.999)) -> torch.Tensor:
     return torch.tensor([lr, 1.0 - betas[0] ** step, math.sqrt(1.0 - betas[1] ** step)], dtype=torch.float32)
 
 
+def adamw_workspace(device) -> torch.Tensor:
+    """Zeroed fp32 workspace of the clip + AdamW step (mimic_adamw_workspace() bytes); [0] = squared gradient norm after a step."""
+    return torch.zeros(lib.mimic_adamw_workspace() // 4, dtype=torch.float32, device=device)
+
+
 def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper: torch.Tensor, *, betas=(0.9, 0.999),
                eps=1e-8, grad_mul=1.0, max_norm=0.0, sumsq: Optional[torch.Tensor] = None,
                lr_mul: Optional[torch.Tensor] = None) -> None:
@@ -637,7 +642,7 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper: torch.Tens
     lr_mul: optional fp32 [n] per-element learning-rate multiplier (the reference's scale_lr group)."""
     _require_cuda(param, grad, exp_avg, exp_avg_sq, weight_decay, hyper, lr_mul)
     if sumsq is None:
-        sumsq = torch.empty(1, dtype=torch.float32, device=param.device)
+        sumsq = adamw_workspace(param.device)
     check(lib.mimic_adamw_step_groups(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(weight_decay),
                                       _ptr(lr_mul), param.numel(), _ptr(hyper), betas[0], betas[1], eps,
                                       float(grad_mul), float(max_norm), _ptr(sumsq), _stream()),

@@ -14,7 +14,7 @@ for one process per GPU:
 from __future__ import annotations
 
 import math
-from contextlib import nullcontext
+from contextlib import nullcontext, contextmanager
 from typing import Dict, Optional
 
 import torch
@@ -96,7 +96,7 @@ class MimicTrainer:
             # were seeded differently, or loaded different checkpoints, must start from identical parameters
             self.broadcast_state()
         self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)       # lr, bias corrections (device: graph replay)
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = ops.adamw_workspace(dev) if dev.type == "cuda" else torch.zeros(1, dtype=torch.float32, device=dev)
         self.opt_step = 0
         self.micro = 0
         self._scalar_keys = ["loss", "ce_loss", "ffn_mse_loss"]     # slots at the tail of the all-reduce buffer (mimic.yaml
@@ -113,8 +113,27 @@ class MimicTrainer:
             for t in (self.flat.param, self.flat.exp_avg, self.flat.exp_avg_sq):
                 dist.broadcast(t, src=src, group=self.pg)
 
+    @contextmanager
     def _on_stream(self):
-        return torch.cuda.stream(self.stream) if self.stream is not None else nullcontext()
+        """Run on the trainer's stream, ordered against the caller's: the trainer's stream first waits for what the caller
+        has enqueued (input batches, a loaded checkpoint), and on the way out the caller's stream waits for the trainer's —
+        whoever reads `flat.param` / the loss tensors right after `micro_step` sees the finished step.  (Without the second
+        wait a 2-rank test that all-gathered the parameters on the default stream read them while AdamW was still running
+        on some boxes of the pool.)  Nested use (capture -> _captured_step) and stream capture are left alone."""
+        if self.stream is None:
+            yield
+            return
+        outer = torch.cuda.current_stream(self.stream.device)
+        if outer == self.stream or torch.cuda.is_current_stream_capturing():
+            with torch.cuda.stream(self.stream):
+                yield
+            return
+        self.stream.wait_stream(outer)
+        try:
+            with torch.cuda.stream(self.stream):
+                yield
+        finally:
+            outer.wait_stream(self.stream)
 
     def micro_step(self, inputs: Optional[dict], query_inputs: dict) -> Dict[str, torch.Tensor]:
         with self._on_stream():

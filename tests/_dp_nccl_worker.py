@@ -51,10 +51,20 @@ def main():
     assert all(torch.equal(gathered[0], g) for g in gathered), "initial parameters were not broadcast from rank 0"
     init = tr.flat.param.clone()
     ins, qs = batch(rank)                                  # ... and different data
-    for step in range(2):
+    for step in range(4):                                  # (clipping is active: grad_clip_val = 1.0)
         tr.micro_step(ins, qs)
         dist.all_gather(gathered, tr.flat.param)
-        assert all(torch.equal(gathered[0], g) for g in gathered), f"ranks diverged after step {step + 1}"
+        if not all(torch.equal(gathered[0], g) for g in gathered):
+            # say what diverged: the all-reduced (scaled) gradients, the squared norm behind the clip factor, or the update
+            gg = [torch.empty_like(tr.flat.grad) for _ in range(world)]
+            dist.all_gather(gg, tr.flat.grad.contiguous())
+            nn = [torch.empty(1, device="cuda") for _ in range(world)]
+            dist.all_gather(nn, tr.sumsq[:1].clone())
+            dp = float((gathered[0] - gathered[1]).abs().max())
+            dg = float((gg[0] - gg[1]).abs().max())
+            raise AssertionError(f"ranks diverged after step {step + 1}: max |dparam| {dp:.3e}, max |dgrad| {dg:.3e}, "
+                                 f"norm^2 per rank {[float(x) for x in nn]}, differing params "
+                                 f"{int((gathered[0] != gathered[1]).sum())} of {gathered[0].numel()}")
         if step == 0:
             after_one = tr.flat.param.clone()
             logged = tr.logged_scalars()

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.mimic_abi_version() == 1
+    assert lib.mimic_abi_version() == 2
 
 
 def test_ops_refuse_cpu_tensors():
@@ -254,7 +254,7 @@ int main(void) {
   /* a NULL descriptor / NULL pointers must come back as an error status with a message, not a crash */
   int rc = mimic_shifted_attn_fwd(&d, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
   printf("%d %d %s\\n", mimic_abi_version(), rc != 0, mimic_last_error());
-  return (mimic_abi_version() == 1 && rc != 0 && strlen(mimic_last_error()) > 0) ? 0 : 1;
+  return (mimic_abi_version() == 2 && rc != 0 && strlen(mimic_last_error()) > 0) ? 0 : 1;
 }
 ''')
     exe = tmp_path / "abi"
