@@ -26,6 +26,8 @@ class AttnDesc(C.Structure):
                 ("dtype", C.c_int32), ("impl", C.c_int32)]
 
 
+ABI_VERSION = 2          # MIMIC_ABI_VERSION of include/mimic_b200.h this front-end was written against
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mimic_abi_version": (C.c_int, []),
@@ -101,8 +103,8 @@ def _load() -> C.CDLL:
         import warnings
         warnings.warn(f"binding a STALE libmimic_b200.so (MIMIC_ALLOW_STALE_LIB set); rebuild failed: {e}", RuntimeWarning)
     lib = _bind(LIB_PATH)             # AttributeError when a prebuilt library is older than the header
-    if lib.mimic_abi_version() != 2:
-        raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != 2; rebuild (python -m mimic_b200.build --force)")
+    if lib.mimic_abi_version() != ABI_VERSION:
+        raise ImportError(f"libmimic_b200.so ABI {lib.mimic_abi_version()} != {ABI_VERSION}; rebuild (python -m mimic_b200.build --force)")
     return lib
 
 
