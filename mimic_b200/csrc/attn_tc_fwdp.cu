@@ -44,12 +44,13 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.f;
 constexpr int OFF_Q = 0, OFF_K = 2 * TILE, OFF_V = 4 * TILE, OFF_OST = 6 * TILE, OFF_BAR = OFF_OST + HALF;
 constexpr int NSCHED = 3;                        // depth of the item ring between the scheduler thread and the consumer roles
-constexpr int OFF_TMEM = OFF_BAR + 48 * 8, OFF_SCHED = OFF_TMEM + 16, OFF_STATS = OFF_SCHED + 16, OFF_KBITS = OFF_STATS + 2 * 128 * 8;
+constexpr int OFF_TMEM = OFF_BAR + 48 * 8, OFF_SCHED = OFF_TMEM + 16, OFF_STATS = OFF_SCHED + 16, OFF_SHIFT = OFF_STATS + 2 * 128 * 8,
+              OFF_KBITS = OFF_SHIFT + HD * 4;
 constexpr int KBITS_MAX = 16384;
 constexpr int SMEM_MAX = OFF_KBITS + KBITS_MAX;
 static_assert(SMEM_MAX <= 227 * 1024, "shared memory budget");
 enum { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 6, V_FULL = 8, V_EMPTY = 10, S_FULL = 12, SOFT_DONE = 14,
-       PV_DONE = 16, O_FULL = 18, O_EMPTY = 20, ST_FULL = 22, ST_EMPTY = 24, SCHED_FULL = 26, SCHED_EMPTY = 30, P_PART = 34 };
+       PV_DONE = 16, O_FULL = 18, O_EMPTY = 20, ST_FULL = 22, ST_EMPTY = 24, SCHED_FULL = 26, SCHED_EMPTY = 30, P_PART = 34, Z_FULL = 42 };
 constexpr int SCHED_CONSUMERS = 8 + 4 + 1 + 3;   // softmax warps, epilogue warps, MMA warp, the K / V / Q producer threads
 constexpr uint32_t IDESC_QK = idesc_bf16(BM, BN, 0, 0);
 constexpr uint32_t IDESC_PV = idesc_bf16(BM, HD, 0, 1);
@@ -87,6 +88,9 @@ struct FwdCounts {       // what the MMA issuer needs of an item
   int jd[2], n[2], nmax, nv;
 };
 
+// DBG = true builds the instrumented twin (per-item %globaltimer stamps of CTA 0, scripts/trace_fwdp_items.py); the
+// production instantiation carries none of it.
+template <bool DBG>
 __global__ void __launch_bounds__(fp::THREADS, 1)
 attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, AttnParams p,
@@ -102,6 +106,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   volatile int* sched = reinterpret_cast<volatile int*>(smem + OFF_SCHED);   // item ring written by the scheduler thread
   float2* stats = reinterpret_cast<float2*>(smem + OFF_STATS);          // [2][128] (1 / l_c, mu)
+  float* s_shift = reinterpret_cast<float*>(smem + OFF_SHIFT);          // shift[h] of the epilogue's current item
   uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_KBITS);  // [B][words] when a key mask is given
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,7 +174,8 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars[Q_FULL + i], 1);
-        mbar_init(&bars[Q_EMPTY + i], 1 + 128);      // last QK^T of the item (commit) + the tile's softmax threads (z1 read)
+        mbar_init(&bars[Q_EMPTY + i], 1 + 128);      // last QK^T of the item (commit) + the epilogue threads (z1 read)
+        mbar_init(&bars[Z_FULL + i], 128);           // z1 of the tile's rows is in stats[].y (epilogue threads)
         mbar_init(&bars[K_FULL + i], 1);
         mbar_init(&bars[K_EMPTY + i], 1);
         mbar_init(&bars[V_FULL + i], 1);
@@ -219,6 +225,16 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // debug timeline: trace[(role * 16 + item ordinal) * 16 + event] in ns; roles 0 MMA issuer, 1 epilogue, 2 / 3 softmax tile 0 / 1
+  auto stamp = [&](int role, uint32_t k, int ev) {
+    if constexpr (DBG) {
+      if (blockIdx.x == 0 && p.trace != nullptr && k < 16) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(role * 16 + k) * 16 + ev] = t;
+      }
+    }
+  };
 
   if (warp == 13 || warp == 14) {
     // ===================== K producer (warp 13) / V producer (warp 14): one thread each, blocking waits =====================
@@ -357,9 +373,11 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       int it_next = n_items;
       bool has_next = false, have_nx = false;
       FwdCounts nx = m;
+      if (lane == 0) stamp(0, k, 0);
       if (m.n[0] > 0 && !pre0) issue_qk(0, m.n[0], m.n[1], 0, kb);
       if (m.n[1] > 0 && !pre1) issue_qk(1, m.n[1], m.n[1], 0, kb);
       pre0 = pre1 = false;
+      if (lane == 0) stamp(0, k, 1);
       for (int j = 0; j < m.nmax; ++j) {
         if (!have_nx && j >= m.nmax - 2) {
           it_next = sched_get(k + 1);
@@ -375,7 +393,11 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (j <= m.jd[x]) {
             // what PV_x(j) needs besides P — the V tile and, for the first PV of an item, a drained O_x — is confirmed BEFORE
             // the softmax hand-over, so that nothing but the issue itself follows it (neither depends on this softmax step)
-            if (j == 0) mbar_wait_q(&bars[O_EMPTY + x], ((x ? oc1 : oc0) & 1) ^ 1);
+            if (j == 0) {
+              if (lane == 0) stamp(0, k, 2 + 2 * x);
+              mbar_wait_q(&bars[O_EMPTY + x], ((x ? oc1 : oc0) & 1) ^ 1);
+              if (lane == 0) stamp(0, k, 3 + 2 * x);
+            }
             mbar_wait_q(&bars[V_FULL + vs], (g >> 1) & 1);
           }
           if (j <= m.jd[x]) {
@@ -387,6 +409,8 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               mbar_wait_q(&bars[P_PART + 4 * x + q], (x ? pp1 : pp0) & 1);
+              if (j == 0 && q == 0 && lane == 0) stamp(0, k, 6 + x);
+              if (j == m.jd[x] && q == 3 && lane == 0) stamp(0, k, 13 + x);
               tc_fence_after();
               if (elect_one()) {
 #pragma unroll
@@ -412,7 +436,9 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (j + 1 < m.n[x]) {
             issue_qk(x, m.n[x], m.n[1], j + 1, kb);
           } else if (has_next && nx.n[x] > 0) {
+            if (lane == 0) stamp(0, k, 9 + 2 * x);
             issue_qk(x, nx.n[x], nx.n[1], 0, kb + m.nmax);               // next item's first scores, behind PV_x(last)
+            if (lane == 0) stamp(0, k, 10 + 2 * x);
             if (x) pre1 = true; else pre0 = true;
           }
         }
@@ -425,6 +451,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       vb += m.nv;
       m = nx;
       it = it_next;
+      if (lane == 0) stamp(0, k, 8);
       sched_release(k);
     }
   } else if (warp >= 8) {
@@ -434,16 +461,53 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool issuer = threadIdx.x == 256;
-    uint32_t oc[2] = {0, 0}, stc[2] = {0, 0};
+    uint32_t oc[2] = {0, 0}, stc[2] = {0, 0}, qce[2] = {0, 0};
     for (uint32_t k = 0;; ++k) {
       const int it = sched_get(k);
       if (it >= n_items) break;
       const FwdItem m = decode(it);
+      if (issuer) stamp(1, k, 0);
+      // shift[h] into shared memory while the item is still being computed (the epilogue proper only starts when the
+      // softmax warps publish the row statistics at the item's end; eight dependent global loads per 32-column chunk
+      // inside it cost ~2.4 us per tile — the MMA issuer sat that long in front of the next item's first PV).  The last
+      // named barrier of the previous item lies behind every read of the row.
+      s_shift[r] = p.active ? __ldg(p.shift + m.h * HD + r) : 0.f;
+      // z1 = q_t . w[h] + bias[h] of both query tiles — only needed for mu at the item's END — is formed HERE, by the
+      // warpgroup that idles while the item is computed: on the softmax warps it cost ~2 us of every item (they are the
+      // busiest resource of the kernel: anything on them is on the critical path).  It travels in the .y slot of the row's
+      // statistics entry (free until the softmax thread writes (1 / l, mu) there at the item's end).
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if ((x ? m.n[1] : m.n[0]) == 0) continue;          // (no Q load for such a tile: same rule as the Q producer)
+        mbar_wait_q(&bars[Q_FULL + x], qce[x] & 1);
+        ++qce[x];
+        if (p.active) {
+          const float4* w4 = reinterpret_cast<const float4*>(p.w + m.h * HD);
+          const uint8_t* sQx = sQ + x * TILE;
+          float za = 0.f, zb = 0.f, zc = 0.f, zd = 0.f;      // four independent chains
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {                    // (64 registers here: two chunks in flight, not sixteen)
+              const uint4 u = *reinterpret_cast<const uint4*>(sQx + hf * HALF + r * 128 + ((c ^ (r & 7)) << 4));
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const float4 wa = __ldg(w4 + (hf * 64 + c * 8) / 4), wb = __ldg(w4 + (hf * 64 + c * 8) / 4 + 1);
+              const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
+              const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
+              za = fmaf(f0.x, wa.x, za); zb = fmaf(f0.y, wa.y, zb); zc = fmaf(f1.x, wa.z, zc); zd = fmaf(f1.y, wa.w, zd);
+              za = fmaf(f2.x, wb.x, za); zb = fmaf(f2.y, wb.y, zb); zc = fmaf(f3.x, wb.z, zc); zd = fmaf(f3.y, wb.w, zd);
+            }
+          stats[x * 128 + r].y = (za + zb) + (zc + zd) + __ldg(p.bias + m.h);
+          mbar_arrive(&bars[Z_FULL + x]);
+        }
+        mbar_arrive(&bars[Q_EMPTY + x]);                   // this thread no longer reads sQ_x
+      }
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         if (m.t0[x] >= T) continue;
         const bool has_pv = m.jd[x] >= 0;
         mbar_wait_q(&bars[ST_FULL + x], stc[x] & 1);
+        if (issuer) stamp(1, k, 1 + 4 * x);
         const float2 st = stats[x * 128 + r];
         mbar_arrive(&bars[ST_EMPTY + x]);
         ++stc[x];
@@ -451,9 +515,10 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mbar_wait_q(&bars[O_FULL + x], oc[x] & 1);
           tc_fence_after();
         }
+        if (issuer) stamp(1, k, 2 + 4 * x);
         const float inv = st.x, mu = st.y;
         const uint32_t t_O = tmem_base + lane_off + 256 + x * BN;
-        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + (p.active ? m.h * HD : 0));
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           if (issuer) bulk_wait_read0();                   // the previous store has finished reading the staging tile
@@ -472,14 +537,11 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if (hf == 1 && c32 == 1 && has_pv) {           // O_x is in registers: the next item's PV_x(0) may overwrite it
               tc_fence_before();
               mbar_arrive(&bars[O_EMPTY + x]);
+              if (issuer) stamp(1, k, 3 + 4 * x);
             }
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-              float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-              if (p.active) {
-                s0 = __ldg(sh4 + (hf * 64 + c32 * 32 + c8 * 8) / 4);
-                s1 = __ldg(sh4 + (hf * 64 + c32 * 32 + c8 * 8) / 4 + 1);
-              }
+              const float4 s0 = sh4[(hf * 64 + c32 * 32 + c8 * 8) / 4], s1 = sh4[(hf * 64 + c32 * 32 + c8 * 8) / 4 + 1];
               uint32_t pk[4];
               pk[0] = pack_bf16(fmaf(o[8 * c8 + 0], inv, mu * s0.x), fmaf(o[8 * c8 + 1], inv, mu * s0.y));
               pk[1] = pack_bf16(fmaf(o[8 * c8 + 2], inv, mu * s0.z), fmaf(o[8 * c8 + 3], inv, mu * s0.w));
@@ -497,6 +559,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         if (has_pv) ++oc[x];
+        if (issuer) stamp(1, k, 4 + 4 * x);
       }
       sched_release(k);
     }
@@ -511,7 +574,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t t_S = tmem_base + lane_off + x * BN, t_O = tmem_base + lane_off + 256 + x * BN;
     const float scale2 = p.scale * LOG2E;
     const uint8_t* sQx = sQ + x * TILE;
-    uint32_t sc = 0, pvc = 0, qc = 0, stc = 0;
+    uint32_t sc = 0, pvc = 0, zc = 0, stc = 0;
 
     for (uint32_t k = 0;; ++k) {
       const int it = sched_get(k);
@@ -528,28 +591,8 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t* kbits = have_kbits ? kbits_all + b * words : nullptr;
 
       float z1 = 0.f;
-      if (nloc > 0) {
-        mbar_wait_q(&bars[Q_FULL + x], qc & 1);
-        ++qc;
-        if (p.active) {
-          const float4* w4 = reinterpret_cast<const float4*>(p.w + h * HD);
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 u = *reinterpret_cast<const uint4*>(sQx + hf * HALF + r * 128 + ((c ^ (r & 7)) << 4));
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-              const float4 wa = __ldg(w4 + (hf * 64 + c * 8) / 4), wb = __ldg(w4 + (hf * 64 + c * 8) / 4 + 1);
-              const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
-              const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
-              z1 = fmaf(f0.x, wa.x, z1); z1 = fmaf(f0.y, wa.y, z1); z1 = fmaf(f1.x, wa.z, z1); z1 = fmaf(f1.y, wa.w, z1);
-              z1 = fmaf(f2.x, wb.x, z1); z1 = fmaf(f2.y, wb.y, z1); z1 = fmaf(f3.x, wb.z, z1); z1 = fmaf(f3.y, wb.w, z1);
-            }
-          z1 += __ldg(p.bias + h);
-        }
-        mbar_arrive(&bars[Q_EMPTY + x]);                   // this thread no longer reads sQ_x
-      }
-
+      const bool tr_thread = r == 0;
+      if (tr_thread) stamp(2 + x, k, 0);
       float m_c = -INFINITY, l_c = 0.f, m_x = -INFINITY, l_x = 0.f;   // log2 domain
       // Per-step tile class, decided with WARP-UNIFORM arithmetic on the warp's 32 rows [tw0, tw0 + 31] — the mask-free
       // classes never touch a per-thread mask word (the word / vote version of this cost ~430 cycles of every step):
@@ -575,6 +618,9 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const bool c_excl = p.active && none_vis && in_range_all && rows_all_ok;
         const bool c_zero = !p.active && none_vis;
         mbar_wait_q(&bars[S_FULL + x], sc & 1);
+        if (tr_thread && j == 0) stamp(2 + x, k, 3);
+        if (tr_thread && j == 1) stamp(2 + x, k, 4);
+        if (tr_thread && j == nloc - 1) stamp(2 + x, k, 9);
         ++sc;
         tc_fence_after();
         if (c_full) {
@@ -797,9 +843,15 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
 
       // ---- item end: row statistics -> epilogue warpgroup (shared memory) and global ----
+      if (tr_thread) stamp(2 + x, k, 5);
       const float inv = l_c > 0.f ? 1.f / l_c : 0.f;
       const float lse_c = l_c > 0.f ? (m_c + log2f(l_c)) * LN2 : -INFINITY;
       float mu = 0.f, lse_full = 0.f;
+      if (p.active && nloc > 0) {                          // z1 of this row, formed by the epilogue warpgroup at the item's start
+        mbar_wait_q(&bars[Z_FULL + x], zc & 1);
+        ++zc;
+        z1 = stats[x * 128 + r].y;
+      }
       if (p.active) {
         const float lse_x = l_x > 0.f ? (m_x + log2f(l_x)) * LN2 : -INFINITY;
         const float hi = fmaxf(lse_c, lse_x), lo = fminf(lse_c, lse_x);
@@ -807,6 +859,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mu = 1.f / (1.f + __expf(lse_full - z1));
       }
       mbar_wait_q(&bars[ST_EMPTY + x], (stc & 1) ^ 1);   // the epilogue has read the previous item's statistics
+      if (tr_thread) stamp(2 + x, k, 6);
       stats[x * 128 + r] = make_float2(inv, mu);
       mbar_arrive(&bars[ST_FULL + x]);
       ++stc;
@@ -818,6 +871,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           p.mu[ridx] = mu;
         }
       }
+      if (tr_thread) stamp(2 + x, k, 7);
       sched_release(k);
     }
   }
@@ -851,7 +905,8 @@ int fwdp(const AttnParams& p, cudaStream_t st) {
   const size_t smem = OFF_KBITS + (p.key_mask ? (size_t)p.B * kbit_words(p.S) * 4 : 0);
   static size_t configured = 0;
   if (smem > configured) {
-    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    MIMIC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     configured = SMEM_MAX;
   }
   // section = (head, batch) streams whose K + V fit the L2 budget together (GQA groups kept whole)
@@ -869,7 +924,13 @@ int fwdp(const AttnParams& p, cudaStream_t st) {
   unsigned int* tickets = nullptr;
   MIMIC_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_fwdp_tickets));
   unsigned int* ticket = tickets + 2 * (seq.fetch_add(1) % N_TICKETS);
-  attn_fwd_tcp_kernel<<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec, ticket);
+  if (debug_trace_capacity() >= 4 * 16 * 16) {
+    AttnParams pp = p;
+    pp.trace = debug_trace_buffer();
+    attn_fwd_tcp_kernel<true><<<grid, THREADS, smem, st>>>(tq, tk, tv, to, pp, (int)sec, ticket);
+  } else {
+    attn_fwd_tcp_kernel<false><<<grid, THREADS, smem, st>>>(tq, tk, tv, to, p, (int)sec, ticket);
+  }
   MIMIC_LAUNCH_OK("attn_fwd_tcp_kernel");
   return MIMIC_OK;
 }
