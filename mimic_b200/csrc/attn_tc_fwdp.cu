@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "attn_common.cuh"
 #include "tc_host.cuh"
@@ -56,6 +57,9 @@ constexpr uint32_t IDESC_QK = idesc_bf16(BM, BN, 0, 0);
 constexpr uint32_t IDESC_PV = idesc_bf16(BM, HD, 0, 1);
 // 512 threads launch with 128 registers each (ptxas sizes a kernel that uses setmaxnreg by whole warpgroups); the epilogue
 // warpgroup and the warpgroup of the two single-thread roles give registers back, the two softmax warpgroups take them
+#ifndef FWDP_EXCL_POLY_MASK
+#define FWDP_EXCL_POLY_MASK 0xA4A4u      // pairs 2, 5, 7 of every 8: three eighths of the exponentials of an exponent-sum-only step
+#endif
 #ifndef FWDP_REG_S
 #define FWDP_REG_S 192
 #define FWDP_REG_E 64
@@ -668,12 +672,22 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_ld32(t_S + 64, *reinterpret_cast<float(*)[32]>(s + 64));
           tmem_ld32(t_S + 96, *reinterpret_cast<float(*)[32]>(s + 96));
           tc_wait_ld();
+          if (!has_pv) {
+            // The scores are in registers and this step writes no P: S_x is free NOW — QK_x(j+1) runs under this step's
+            // exponentials instead of behind them.  (Above the diagonal of an active handle every step is of this kind:
+            // 1.8 us per pair of tiles for 0.55 us of MMA before the early release.)
+            tc_fence_before();
+            mbar_arrive(&bars[SOFT_DONE + x]);
+          }
           const float mx_new = fmaxf(m_x, row_max128(s) * scale2);
           const float carry = (m_x == -INFINITY) ? 0.f : l_x * ex2(m_x - mx_new);
-          l_x = carry + (expsum32(*reinterpret_cast<const float(*)[32]>(s), scale2, -mx_new) +
-                         expsum32(*reinterpret_cast<const float(*)[32]>(s + 32), scale2, -mx_new)) +
-                (expsum32(*reinterpret_cast<const float(*)[32]>(s + 64), scale2, -mx_new) +
-                 expsum32(*reinterpret_cast<const float(*)[32]>(s + 96), scale2, -mx_new));
+          // three eighths of these exponentials go to the FMA pipe (expsum32_poly): measured 0.56 -> 0.58-0.59 of burst at
+          // T = 4096 and 0.59-0.60 -> 0.61-0.63 at T = 8192; 1/4: less, 1/2: the same, 5/8: slower than none
+          constexpr uint32_t PM = FWDP_EXCL_POLY_MASK;
+          l_x = carry + (expsum32_poly<PM>(*reinterpret_cast<const float(*)[32]>(s), scale2, -mx_new) +
+                         expsum32_poly<PM>(*reinterpret_cast<const float(*)[32]>(s + 32), scale2, -mx_new)) +
+                (expsum32_poly<PM>(*reinterpret_cast<const float(*)[32]>(s + 64), scale2, -mx_new) +
+                 expsum32_poly<PM>(*reinterpret_cast<const float(*)[32]>(s + 96), scale2, -mx_new));
           m_x = mx_new;
           if (has_pv) {                                    // (cannot happen above the diagonal of this tile; kept for safety)
             uint32_t z[16];
@@ -836,7 +850,7 @@ attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         if (has_pv) {
           ++pvc;                                             // the four P_PART arrivals of the step stand for SOFT_DONE
-        } else {
+        } else if (!c_excl || c_full) {                      // (an exponent-sum-only step released S_x right after loading it)
           tc_fence_before();
           mbar_arrive(&bars[SOFT_DONE + x]);
         }

@@ -107,6 +107,44 @@ __device__ __forceinline__ float max32(const float (&s)[32]) {
     for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], fmaxf(s[8 * k + c], s[8 * k + c + 1]));
   return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
 }
+// The same sum with the pairs selected by MASK (bit c2 = columns 2 c2, 2 c2 + 1) exponentiated on the FMA pipe instead of
+// the MUFU: 2^a = 2^n 2^r with n = round(a) (magic-number add), r in [-0.5, 0.5], 2^r by a degree-3 polynomial (relative
+// error 7.5e-5), the exponent added with an integer shift-add.  For the exponent-SUM-only steps above the diagonal of an
+// active handle: they write no P, so their warps have issue slots to spare while the MUFU (one warp instruction per 8
+// cycles per sub-partition, shared by the two tiles' warps) is what bounds them.
+template <uint32_t MASK>
+__device__ __forceinline__ float expsum32_poly(const float (&s)[32], float scale2, float neg_m) {
+  const float2 sc = make_float2(scale2, scale2), ng = make_float2(neg_m, neg_m);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 c3 = make_float2(0.05517027899622917f, 0.05517027899622917f), c2v = make_float2(0.2426076978445053f, 0.2426076978445053f);
+  const float2 c1 = make_float2(0.693260908126831f, 0.693260908126831f), c0 = make_float2(0.9999282956123352f, 0.9999282956123352f);
+  float2 sum[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sum[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c2 = 0; c2 < 16; ++c2) {
+    float2 a = __ffma2_rn(make_float2(s[2 * c2], s[2 * c2 + 1]), sc, ng);
+    float2 e;
+    if ((MASK >> c2) & 1u) {
+      a.x = fmaxf(a.x, -126.f);
+      a.y = fmaxf(a.y, -126.f);
+      const float2 t = __fadd2_rn(a, magic);                 // integer part in the low mantissa bits
+      const float2 n = __fadd2_rn(t, nmagic);
+      const float2 r = __fadd2_rn(a, make_float2(-n.x, -n.y));
+      float2 q = __ffma2_rn(r, c3, c2v);
+      q = __ffma2_rn(q, r, c1);
+      q = __ffma2_rn(q, r, c0);
+      e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+      e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    } else {
+      e = make_float2(ptx::ex2(a.x), ptx::ex2(a.y));
+    }
+    sum[c2 & 3] = __fadd2_rn(sum[c2 & 3], e);
+  }
+  const float2 tt = __fadd2_rn(__fadd2_rn(sum[0], sum[1]), __fadd2_rn(sum[2], sum[3]));
+  return tt.x + tt.y;
+}
+
 __device__ __forceinline__ float expsum32(const float (&s)[32], float scale2, float neg_m) {
   const float2 sc = make_float2(scale2, scale2), ng = make_float2(neg_m, neg_m);
   float2 sum[4];
