@@ -39,7 +39,7 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the context-pass forward at the Idefics2 shape
-TRAFFIC_BYTES = 94.77e6     # 78.79 MB read + 15.99 MB written per launch
+TRAFFIC_BYTES = 93.74e6     # 78.79 MB read + 14.95 MB written per launch
 TRAFFIC_SOURCE = "profiles/r02_ncu_kernels.md (ncu --set full, attn_fwd_tc64p_kernel at the context-pass shape)"
 
 
