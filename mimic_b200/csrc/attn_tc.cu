@@ -453,7 +453,7 @@ bool fwdp_supports(const AttnParams& p, bool forced);
 
 // Forward kernel choice.  MIMIC_FWD_KERNEL (read ONCE per process; A/B scripts set it before the first call) forces a family:
 // "1" single-tile, 128-key tiles / "3" 64-key tiles, two CTAs per SM (persistent when it pays) / "4" that one persistent
-// always / "5" never persistent / "6" persistent ping-pong.  Default: 6 from 2048 query rows on, else 3.  (The one-item-per-CTA ping-pong and
+// always / "5" never persistent / "6" persistent ping-pong.  Default: 6 from 1024 (active) / 3072 (inactive) query rows on, 4 for a padded context pass, else 3.  (The one-item-per-CTA ping-pong and
 // the eight-softmax-warp experiments of round 1 were measured slower everywhere and are gone: DESIGN.md §4.)
 static int g_forced_fwd = -1;            // mimic_debug_force_fwd_kernel(); -1 = MIMIC_FWD_KERNEL (read once) or 0
 void force_fwd_kernel(int k) { g_forced_fwd = k; }
