@@ -316,3 +316,19 @@ def test_graft_entry_build_runs():
     import importlib
     ge = importlib.import_module("__graft_entry__")
     ge.build()
+
+
+def test_grad_like_keeps_row_stride_and_alignment():
+    """Gradient buffers of the loss ops: the row stride of the logits view and its address modulo 32 bytes (the kernels
+    address logits and gradient with ONE stride and align their 16-byte chunks on the logits row)."""
+    import torch
+    from mimic_b200.ops import _grad_like
+    wide = torch.zeros(7, 50, dtype=torch.bfloat16)
+    for view in (wide, wide[:, :37], wide[1:, 3:40], wide[2:, 5:6]):
+        g = _grad_like(view)
+        assert g.shape == view.shape and g.dtype == view.dtype
+        if view.shape[0] > 1:
+            assert g.stride(0) == view.stride(0)
+        assert g.stride(1) == 1 and g.data_ptr() % 32 == view.data_ptr() % 32
+        g.fill_(1)                                           # every element addressable inside its own storage
+        assert int(g.float().sum()) == view.numel()
